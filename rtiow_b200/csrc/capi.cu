@@ -1,0 +1,758 @@
+// capi.cu — host side of librtiow_cuda.so: the C ABI of include/rtiow_cuda.h.
+// Replaces the rayon row loop, collect and flip of /root/reference/src/main.rs:122-145 with
+// one call that drives the sm_100a kernels in rt_render.cuh.  No CPU fallback anywhere: with no
+// CUDA device every compute entry point returns RTIOW_ERR_NO_DEVICE.
+#include "../../include/rtiow_cuda.h"
+#include "rt_unit.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace rt;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) return fail(RTIOW_ERR_CUDA, "%s -> %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" int rtiow_abi_version(void) { return RTIOW_ABI_VERSION; }
+extern "C" const char* rtiow_last_error(void) { return g_err.c_str(); }
+extern "C" int rtiow_device_count(int* out)
+{
+    if (!out) return fail(RTIOW_ERR_INVALID_ARG, "out_count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
+    *out = n;
+    return RTIOW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+template <typename U> struct DevBuf {
+    U* p = nullptr; size_t n = 0;
+    cudaError_t resize(size_t count)
+    {
+        if (count <= n && p) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(U));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+struct DeviceState {
+    int device = 0;
+    int sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_done = nullptr;
+    // scene
+    DevBuf<float> soa; DevBuf<float4> small; DevBuf<int> small_idx; DevBuf<double4> big; DevBuf<int> big_idx;
+    DevBuf<float4> sph; DevBuf<double4> sphd; DevBuf<float4> mat; DevBuf<double4> matd; DevBuf<uint8_t> kind;
+    SceneDev scene{};
+    bool has_scene = false;
+    // frame
+    DevBuf<unsigned long long> accum; DevBuf<unsigned long long> counters;   // [0]=work [1]=rays
+    DevBuf<uint32_t> tiles; DevBuf<uint32_t> gathered; DevBuf<uint32_t> frame;
+    uint8_t* pinned = nullptr; size_t pinned_bytes = 0;
+    unsigned long long* pinned_cnt = nullptr;
+    // measurement
+    DevBuf<uint4> flush; DevBuf<float> probe;
+};
+
+struct rtiow_ctx {
+    std::vector<DeviceState> dev;
+    size_t scene_bytes = 0;
+};
+
+static int init_device(DeviceState& d, int device)
+{
+    d.device = device;
+    CU(cudaSetDevice(device));
+    cudaDeviceProp p; CU(cudaGetDeviceProperties(&p, device));
+    if (p.major < 10) return fail(RTIOW_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device, p.major, p.minor);
+    d.sms = p.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&d.ev0)); CU(cudaEventCreate(&d.ev1)); CU(cudaEventCreateWithFlags(&d.ev_done, cudaEventDisableTiming));
+    CU(d.counters.resize(2));
+    CU(cudaMallocHost(&d.pinned_cnt, 2 * sizeof(unsigned long long)));
+    return RTIOW_OK;
+}
+
+static int create_ctx(const std::vector<int>& devices, rtiow_ctx** out)
+{
+    if (!out) return fail(RTIOW_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    int n = 0; rtiow_device_count(&n);
+    if (n == 0) return fail(RTIOW_ERR_NO_DEVICE, "no CUDA device visible (there is no CPU fallback)");
+    for (int dv : devices) if (dv < 0 || dv >= n) return fail(RTIOW_ERR_INVALID_ARG, "device %d out of range (have %d)", dv, n);
+    rtiow_ctx* c = new rtiow_ctx();
+    c->dev.resize(devices.size());
+    for (size_t i = 0; i < devices.size(); ++i) {
+        int rc = init_device(c->dev[i], devices[i]);
+        if (rc != RTIOW_OK) { rtiow_ctx_destroy(c); return rc; }
+    }
+    // peer access for the tile gather over NVLink (single-process multi-GPU)
+    for (size_t i = 1; i < devices.size(); ++i) {
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, devices[i], devices[0]);
+        if (can) { cudaSetDevice(devices[i]); cudaError_t e = cudaDeviceEnablePeerAccess(devices[0], 0); if (e != cudaSuccess) cudaGetLastError(); }
+    }
+    *out = c;
+    return RTIOW_OK;
+}
+
+extern "C" int rtiow_ctx_create(int n_gpus, rtiow_ctx** out)
+{
+    if (n_gpus < 1) return fail(RTIOW_ERR_INVALID_ARG, "n_gpus must be >= 1");
+    std::vector<int> d(n_gpus);
+    for (int i = 0; i < n_gpus; ++i) d[i] = i;
+    return create_ctx(d, out);
+}
+extern "C" int rtiow_ctx_create_on_device(int device, rtiow_ctx** out) { return create_ctx(std::vector<int>{ device }, out); }
+
+extern "C" void rtiow_ctx_destroy(rtiow_ctx* c)
+{
+    if (!c) return;
+    for (auto& d : c->dev) {
+        cudaSetDevice(d.device);
+        if (d.stream) cudaStreamSynchronize(d.stream);
+        d.soa.release(); d.small.release(); d.small_idx.release(); d.big.release(); d.big_idx.release();
+        d.sph.release(); d.sphd.release(); d.mat.release(); d.matd.release(); d.kind.release();
+        d.accum.release(); d.counters.release(); d.tiles.release(); d.gathered.release(); d.frame.release();
+        d.flush.release(); d.probe.release();
+        if (d.pinned) cudaFreeHost(d.pinned);
+        if (d.pinned_cnt) cudaFreeHost(d.pinned_cnt);
+        if (d.ev0) cudaEventDestroy(d.ev0);
+        if (d.ev1) cudaEventDestroy(d.ev1);
+        if (d.ev_done) cudaEventDestroy(d.ev_done);
+        if (d.stream) cudaStreamDestroy(d.stream);
+    }
+    delete c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// scene upload: HittableList (shapes/mod.rs:52) -> device SoA
+// ------------------------------------------------------------------------------------------------
+// spheres with |r| above this go to the f64 list: for them |oc|^2 - r^2 (sphere.rs:22) and the far
+// root of rays leaving the surface lose more than t_min = 1e-4 (main.rs:44) in f32.
+static const double kBigRadius = 8.0;
+
+extern "C" int rtiow_scene_upload(rtiow_ctx* c, const rtiow_spheres* s, const rtiow_materials* m)
+{
+    if (!c || !s || !m) return fail(RTIOW_ERR_INVALID_ARG, "NULL argument");
+    if (s->n > 0 && (!s->cx || !s->cy || !s->cz || !s->radius || !s->mat_index)) return fail(RTIOW_ERR_INVALID_ARG, "NULL sphere array");
+    if (m->n > 0 && (!m->kind || !m->albedo_r || !m->albedo_g || !m->albedo_b || !m->param)) return fail(RTIOW_ERR_INVALID_ARG, "NULL material array");
+    if (s->n > (1u << 30)) return fail(RTIOW_ERR_INVALID_ARG, "too many spheres");
+    const int n = (int)s->n;
+    for (int i = 0; i < n; ++i) {
+        if (s->mat_index[i] >= m->n) return fail(RTIOW_ERR_INVALID_ARG, "sphere %d: material index %u out of range (%u)", i, s->mat_index[i], m->n);
+        if (m->kind[s->mat_index[i]] > RTIOW_MAT_DIELECTRIC) return fail(RTIOW_ERR_UNSUPPORTED, "sphere %d: material kind %u has no GPU implementation", i, m->kind[s->mat_index[i]]);
+        if (!(std::isfinite(s->cx[i]) && std::isfinite(s->cy[i]) && std::isfinite(s->cz[i]) && std::isfinite(s->radius[i])))
+            return fail(RTIOW_ERR_INVALID_ARG, "sphere %d: non-finite centre or radius", i);
+    }
+    std::vector<float4> sph(n), mat(n); std::vector<double4> sphd(n), matd(n); std::vector<uint8_t> kind(n);
+    std::vector<int> small_ids, big_ids;
+    for (int i = 0; i < n; ++i) {
+        const uint32_t mi = s->mat_index[i];
+        sphd[i] = make_double4(s->cx[i], s->cy[i], s->cz[i], s->radius[i]);
+        sph[i] = make_float4((float)s->cx[i], (float)s->cy[i], (float)s->cz[i], (float)s->radius[i]);
+        matd[i] = make_double4(m->albedo_r[mi], m->albedo_g[mi], m->albedo_b[mi], m->param[mi]);
+        mat[i] = make_float4((float)m->albedo_r[mi], (float)m->albedo_g[mi], (float)m->albedo_b[mi], (float)m->param[mi]);
+        kind[i] = (uint8_t)m->kind[mi];
+        const double reach = std::sqrt(s->cx[i] * s->cx[i] + s->cy[i] * s->cy[i] + s->cz[i] * s->cz[i]) + std::fabs(s->radius[i]);
+        if (std::fabs(s->radius[i]) > kBigRadius || reach > 4096.0) big_ids.push_back(i); else small_ids.push_back(i);
+    }
+    const int ns = (int)small_ids.size(), nb = (int)big_ids.size();
+    const int np = (ns + 31) / 32 * 32;
+    if (np > 65536 * 32) return fail(RTIOW_ERR_UNSUPPORTED, "scene too large");
+    std::vector<float> soa((size_t)4 * np); std::vector<float4> small(np); std::vector<int> small_idx(np);
+    for (int p = 0; p < np; ++p) {
+        if (p < ns) {
+            const float4 v = sph[small_ids[p]];
+            soa[p] = v.x; soa[np + p] = v.y; soa[2 * (size_t)np + p] = v.z;
+            // filter radius^2 inflated by 2^-20 (+ a denormal-safe floor): see RT_FILTER_DIR_SCALE
+            soa[3 * (size_t)np + p] = v.w * v.w * 1.00000095367431640625f + 1e-30f;
+            small[p] = v; small_idx[p] = small_ids[p];
+        } else {       // padding: |oc|^2 + 1e30 can never be reached by hb^2
+            soa[p] = 0; soa[np + p] = 0; soa[2 * (size_t)np + p] = 0; soa[3 * (size_t)np + p] = -1e30f;
+            small[p] = make_float4(0, 0, 0, 0); small_idx[p] = -1;
+        }
+    }
+    std::vector<double4> big(nb); for (int b = 0; b < nb; ++b) big[b] = sphd[big_ids[b]];
+    c->scene_bytes = 0;
+    for (auto& d : c->dev) {
+        CU(cudaSetDevice(d.device));
+        CU(d.soa.resize(soa.size())); CU(d.small.resize(np)); CU(d.small_idx.resize(np)); CU(d.big.resize(nb)); CU(d.big_idx.resize(nb));
+        CU(d.sph.resize(n)); CU(d.sphd.resize(n)); CU(d.mat.resize(n)); CU(d.matd.resize(n)); CU(d.kind.resize(n));
+        size_t bytes = 0;
+#define UP(dst, src, cnt, type) do { if ((cnt) > 0) { CU(cudaMemcpyAsync(dst.p, src.data(), (size_t)(cnt) * sizeof(type), cudaMemcpyHostToDevice, d.stream)); bytes += (size_t)(cnt) * sizeof(type); } } while (0)
+        UP(d.soa, soa, soa.size(), float); UP(d.small, small, np, float4); UP(d.small_idx, small_idx, np, int);
+        UP(d.big, big, nb, double4); UP(d.big_idx, big_ids, nb, int);
+        UP(d.sph, sph, n, float4); UP(d.sphd, sphd, n, double4); UP(d.mat, mat, n, float4); UP(d.matd, matd, n, double4); UP(d.kind, kind, n, uint8_t);
+#undef UP
+        CU(cudaStreamSynchronize(d.stream));
+        d.scene.soa = d.soa.p; d.scene.small = d.small.p; d.scene.small_idx = d.small_idx.p; d.scene.np = np;
+        d.scene.big = d.big.p; d.scene.big_idx = d.big_idx.p; d.scene.nb = nb;
+        d.scene.sph = d.sph.p; d.scene.sphd = d.sphd.p; d.scene.mat = d.mat.p; d.scene.matd = d.matd.p; d.scene.kind = d.kind.p; d.scene.n = n;
+        d.has_scene = true;
+        c->scene_bytes = bytes;
+    }
+    return RTIOW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Camera::new (camera.rs:17-45), host f64
+// ------------------------------------------------------------------------------------------------
+struct HV { double x, y, z; };
+static HV hsub(HV a, HV b) { return { a.x - b.x, a.y - b.y, a.z - b.z }; }
+static HV hmul(HV a, double s) { return { a.x * s, a.y * s, a.z * s }; }
+static HV hdiv(HV a, double s) { return hmul(a, 1.0 / s); }                       // vec3.rs:371-376
+static double hlen(HV a) { return std::sqrt(a.x * a.x + a.y * a.y + a.z * a.z); }
+static HV hunit(HV a) { return hdiv(a, hlen(a)); }                                // vec3.rs:107-109
+static HV hcross(HV a, HV b) { return { a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x }; }
+
+extern "C" int rtiow_camera_new(const double look_from[3], const double look_at[3], const double v_up[3], double v_fov_deg,
+                                double aspect_ratio, double aperture, double focus_dist, rtiow_camera* out)
+{
+    if (!look_from || !look_at || !v_up || !out) return fail(RTIOW_ERR_INVALID_ARG, "NULL argument");
+    const HV from = { look_from[0], look_from[1], look_from[2] }, at = { look_at[0], look_at[1], look_at[2] }, up = { v_up[0], v_up[1], v_up[2] };
+    const double theta = v_fov_deg * (3.14159265358979323846264338327950288 / 180.0);   // f64::to_radians, camera.rs:25
+    const double viewport_height = 2.0 * std::tan(theta / 2.0);
+    const double viewport_width = aspect_ratio * viewport_height;
+    const HV w = hunit(hsub(from, at));                                                   // camera.rs:29
+    const HV u = hunit(hcross(up, w));
+    const HV v = hcross(w, u);
+    const HV horizontal = hmul(u, focus_dist * viewport_width);                           // camera.rs:33
+    const HV vertical = hmul(v, focus_dist * viewport_height);
+    const HV llc = hsub(hsub(hsub(from, hdiv(horizontal, 2.0)), hdiv(vertical, 2.0)), hmul(w, focus_dist));  // camera.rs:35
+    auto put = [](double* d, HV a) { d[0] = a.x; d[1] = a.y; d[2] = a.z; };
+    put(out->origin, from); put(out->lower_left_corner, llc); put(out->horizontal, horizontal); put(out->vertical, vertical);
+    put(out->u, u); put(out->v, v); put(out->w, w);
+    out->lens_radius = aperture / 2.0;
+    return RTIOW_OK;
+}
+
+template <typename T> static CameraT<T> to_dev_camera(const rtiow_camera& c)
+{
+    CameraT<T> d;
+    d.origin = mk<T>((T)c.origin[0], (T)c.origin[1], (T)c.origin[2]);
+    d.llc_minus_origin = mk<T>((T)(c.lower_left_corner[0] - c.origin[0]), (T)(c.lower_left_corner[1] - c.origin[1]), (T)(c.lower_left_corner[2] - c.origin[2]));
+    d.horizontal = mk<T>((T)c.horizontal[0], (T)c.horizontal[1], (T)c.horizontal[2]);
+    d.vertical = mk<T>((T)c.vertical[0], (T)c.vertical[1], (T)c.vertical[2]);
+    d.u = mk<T>((T)c.u[0], (T)c.u[1], (T)c.u[2]);
+    d.v = mk<T>((T)c.v[0], (T)c.v[1], (T)c.v[2]);
+    d.lens_radius = (T)c.lens_radius;
+    return d;
+}
+
+extern "C" void rtiow_params_default(rtiow_params* p)
+{
+    if (!p) return;
+    memset(p, 0, sizeof *p);
+    p->width = 200; p->height = 133; p->spp = 100; p->max_depth = 50;     // main.rs:24-28 (200/1.5 truncates to 133)
+    p->t_min = 0.0001;                                                    // main.rs:44
+    p->seed = 1; p->alpha = 255;                                          // main.rs:137
+    p->precision = RTIOW_PRECISION_F32; p->tile_rows = 4;
+}
+
+// ------------------------------------------------------------------------------------------------
+// frame partition
+// ------------------------------------------------------------------------------------------------
+static uint32_t rows_of_rank(uint32_t height, uint32_t tile_rows, uint32_t world, uint32_t rank)
+{
+    const uint32_t n_tiles = (height + tile_rows - 1) / tile_rows;
+    uint32_t rows = 0;
+    for (uint32_t tg = rank; tg < n_tiles; tg += world) rows += std::min(tile_rows, height - tg * tile_rows);
+    return rows;
+}
+static uint32_t max_rows_per_rank(uint32_t height, uint32_t tile_rows, uint32_t world)
+{
+    const uint32_t n_tiles = (height + tile_rows - 1) / tile_rows;
+    return ((n_tiles + world - 1) / world) * tile_rows;
+}
+static int check_params(const rtiow_params* p)
+{
+    if (!p) return fail(RTIOW_ERR_INVALID_ARG, "params is NULL");
+    if (p->width < 2 || p->height < 2) return fail(RTIOW_ERR_INVALID_ARG, "width and height must be >= 2 (jitter divides by W-1, H-1: main.rs:131-132)");
+    if (p->spp == 0) return fail(RTIOW_ERR_INVALID_ARG, "spp must be >= 1");
+    if ((uint64_t)p->width * p->height > 0xfffffff0ull) return fail(RTIOW_ERR_INVALID_ARG, "frame too large");
+    if (p->tile_rows == 0) return fail(RTIOW_ERR_INVALID_ARG, "tile_rows must be >= 1");
+    if (p->precision > RTIOW_PRECISION_F64) return fail(RTIOW_ERR_INVALID_ARG, "unknown precision");
+    if (!(p->t_min >= 0.0)) return fail(RTIOW_ERR_INVALID_ARG, "t_min must be >= 0");
+    return RTIOW_OK;
+}
+
+extern "C" int rtiow_tile_buffer_bytes(const rtiow_params* p, int world, size_t* out)
+{
+    int rc = check_params(p); if (rc) return rc;
+    if (world < 1 || !out) return fail(RTIOW_ERR_INVALID_ARG, "bad world/out");
+    *out = (size_t)max_rows_per_rank(p->height, p->tile_rows, (uint32_t)world) * p->width * 4;
+    return RTIOW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch configuration
+// ------------------------------------------------------------------------------------------------
+struct ScanCfg { int variant; size_t smem; };   // 0: smem 256x4, 1: smem 512x1 (large scenes), 2: global-memory scene
+static size_t cand_bytes(int threads) { return (size_t)threads * RT_CAND_CAP * sizeof(uint16_t); }
+static ScanCfg pick_cfg(int np)
+{
+    const size_t soa = (size_t)np * 16;
+    if (soa + cand_bytes(256) <= 56 * 1024) return { 0, soa + cand_bytes(256) };
+    if (soa + cand_bytes(512) <= 227 * 1024) return { 1, soa + cand_bytes(512) };
+    return { 2, cand_bytes(256) };
+}
+
+template <typename K> static int prep_kernel(K kernel, size_t smem, int threads, int sms, int* grid)
+{
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    if (per_sm < 1) return fail(RTIOW_ERR_CUDA, "kernel does not fit on an SM (smem %zu)", smem);
+    *grid = per_sm * sms;
+    return RTIOW_OK;
+}
+
+template <typename T>
+static int launch_render(DeviceState& d, const rtiow_camera* cam, const rtiow_params* p, uint32_t rank, uint32_t world, uint32_t* d_tiles,
+                         cudaStream_t st, uint32_t* launches)
+{
+    RenderArgs<T> a;
+    a.scene = d.scene; a.cam = to_dev_camera<T>(*cam);
+    a.width = p->width; a.height = p->height; a.spp = p->spp; a.max_depth = p->max_depth; a.t_min = (T)p->t_min; a.seed = p->seed;
+    a.rank = rank; a.world = world; a.tile_rows = p->tile_rows; a.local_rows = rows_of_rank(p->height, p->tile_rows, world, rank);
+    a.chunk_samples = std::min<uint32_t>(p->spp, 256u);
+    a.chunks_per_pixel = (p->spp + a.chunk_samples - 1) / a.chunk_samples;
+    a.chunks_per_fetch = std::max<uint32_t>(1u, 256u / a.chunk_samples);
+    const uint64_t n_lp = (uint64_t)a.local_rows * p->width;
+    a.n_chunks = n_lp * a.chunks_per_pixel;
+    CU(d.accum.resize(3 * n_lp));
+    a.accum = d.accum.p; a.work_counter = d.counters.p; a.ray_counter = d.counters.p + 1; a.np_smem = 1;
+    CU(cudaMemsetAsync(d.accum.p, 0, 3 * n_lp * sizeof(unsigned long long), st));
+    CU(cudaMemsetAsync(d.counters.p, 0, 2 * sizeof(unsigned long long), st));
+    if (n_lp == 0) return RTIOW_OK;
+    int grid = 0;
+    if (sizeof(T) == 8) {
+        auto k = render_kernel<T, false, 256, 2>;
+        int rc = prep_kernel(k, 0, 256, d.sms, &grid); if (rc) return rc;
+        k<<<grid, 256, 0, st>>>(a);
+    } else {
+        const ScanCfg cfg = pick_cfg(d.scene.np);
+        if (cfg.variant == 0) {
+            auto k = render_kernel<T, true, 256, 4>;
+            int rc = prep_kernel(k, cfg.smem, 256, d.sms, &grid); if (rc) return rc;
+            k<<<grid, 256, cfg.smem, st>>>(a);
+        } else if (cfg.variant == 1) {
+            auto k = render_kernel<T, true, 512, 1>;
+            int rc = prep_kernel(k, cfg.smem, 512, d.sms, &grid); if (rc) return rc;
+            k<<<grid, 512, cfg.smem, st>>>(a);
+        } else {
+            auto k = render_kernel<T, false, 256, 4>;
+            int rc = prep_kernel(k, cfg.smem, 256, d.sms, &grid); if (rc) return rc;
+            k<<<grid, 256, cfg.smem, st>>>(a);
+        }
+    }
+    CU(cudaGetLastError());
+    finalize_kernel<<<(unsigned)((n_lp + 255) / 256), 256, 0, st>>>(d.accum.p, (uint32_t)n_lp, p->spp, p->alpha, d_tiles);
+    CU(cudaGetLastError());
+    *launches += 2;
+    return RTIOW_OK;
+}
+
+static int render_tiles(DeviceState& d, const rtiow_camera* cam, const rtiow_params* p, uint32_t rank, uint32_t world, uint32_t* d_tiles,
+                        cudaStream_t st, uint32_t* launches)
+{
+    if (!d.has_scene) return fail(RTIOW_ERR_INVALID_ARG, "no scene uploaded (call rtiow_scene_upload first)");
+    CU(cudaSetDevice(d.device));
+    return p->precision == RTIOW_PRECISION_F64 ? launch_render<double>(d, cam, p, rank, world, d_tiles, st, launches)
+                                               : launch_render<float>(d, cam, p, rank, world, d_tiles, st, launches);
+}
+
+static double now_ms()
+{
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+extern "C" int rtiow_render_tiles_device(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_params* p, int rank, int world, void* d_tiles,
+                                         void* stream, rtiow_stats* stats)
+{
+    if (!c || !cam || !d_tiles) return fail(RTIOW_ERR_INVALID_ARG, "NULL argument");
+    int rc = check_params(p); if (rc) return rc;
+    if (world < 1 || rank < 0 || rank >= world) return fail(RTIOW_ERR_INVALID_ARG, "bad rank/world");
+    DeviceState& d = c->dev[0];
+    CU(cudaSetDevice(d.device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : d.stream;
+    const double t0 = now_ms();
+    uint32_t launches = 0;
+    if (stats) CU(cudaEventRecord(d.ev0, st));
+    rc = render_tiles(d, cam, p, (uint32_t)rank, (uint32_t)world, (uint32_t*)d_tiles, st, &launches); if (rc) return rc;
+    if (stats) {
+        CU(cudaEventRecord(d.ev1, st));
+        CU(cudaMemcpyAsync(d.pinned_cnt, d.counters.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        float ms = 0; CU(cudaEventElapsedTime(&ms, d.ev0, d.ev1));
+        memset(stats, 0, sizeof *stats);
+        stats->kernel_ms = ms; stats->total_ms = now_ms() - t0;
+        stats->paths = (uint64_t)rows_of_rank(p->height, p->tile_rows, world, rank) * p->width * p->spp;
+        stats->rays_traced = d.pinned_cnt[1]; stats->sphere_tests = stats->rays_traced * (uint64_t)d.scene.n;
+        stats->kernel_launches = launches; stats->n_gpus = 1;
+    }
+    return RTIOW_OK;
+}
+
+extern "C" int rtiow_deinterleave_device(rtiow_ctx* c, const void* d_gathered, const rtiow_params* p, int world, void* d_frame, void* stream)
+{
+    if (!c || !d_gathered || !d_frame) return fail(RTIOW_ERR_INVALID_ARG, "NULL argument");
+    int rc = check_params(p); if (rc) return rc;
+    if (world < 1) return fail(RTIOW_ERR_INVALID_ARG, "bad world");
+    DeviceState& d = c->dev[0];
+    CU(cudaSetDevice(d.device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : d.stream;
+    const size_t npx = (size_t)p->width * p->height;
+    const size_t tile_px = (size_t)max_rows_per_rank(p->height, p->tile_rows, world) * p->width;
+    deinterleave_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, st>>>((const uint32_t*)d_gathered, p->width, p->height, p->tile_rows, (uint32_t)world, tile_px, (uint32_t*)d_frame);
+    CU(cudaGetLastError());
+    return RTIOW_OK;
+}
+
+// THE drop-in call (main.rs:122-145)
+extern "C" int rtiow_render(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_params* p, uint8_t* out_rgba, rtiow_stats* stats)
+{
+    if (!c || !cam || !out_rgba) return fail(RTIOW_ERR_INVALID_ARG, "NULL argument");
+    int rc = check_params(p); if (rc) return rc;
+    const double t0 = now_ms();
+    const uint32_t world = (uint32_t)c->dev.size();
+    const size_t frame_bytes = (size_t)p->width * p->height * 4;
+    const size_t tile_px = (size_t)max_rows_per_rank(p->height, p->tile_rows, world) * p->width;
+    DeviceState& d0 = c->dev[0];
+    uint32_t launches = 0;
+    CU(cudaSetDevice(d0.device));
+    if (d0.pinned_bytes < frame_bytes) {
+        if (d0.pinned) cudaFreeHost(d0.pinned);
+        d0.pinned = nullptr; d0.pinned_bytes = 0;
+        CU(cudaMallocHost(&d0.pinned, frame_bytes)); d0.pinned_bytes = frame_bytes;
+    }
+    const uint32_t* d_final = nullptr;
+    if (world == 1) {
+        CU(d0.tiles.resize(tile_px));
+        CU(cudaEventRecord(d0.ev0, d0.stream));
+        rc = render_tiles(d0, cam, p, 0, 1, d0.tiles.p, d0.stream, &launches); if (rc) return rc;
+        CU(cudaEventRecord(d0.ev1, d0.stream));
+        d_final = d0.tiles.p;                                  // world == 1: rank-local order IS top-down
+    } else {
+        // interleaved row tiles on every GPU, gathered into device 0 over NVLink peer copies
+        CU(d0.gathered.resize(tile_px * world)); CU(d0.frame.resize((size_t)p->width * p->height));
+        for (uint32_t r = 0; r < world; ++r) {
+            DeviceState& d = c->dev[r];
+            CU(cudaSetDevice(d.device));
+            uint32_t* dst = nullptr;
+            if (r == 0) dst = d0.gathered.p; else { CU(d.tiles.resize(tile_px)); dst = d.tiles.p; }
+            if (r == 0) CU(cudaEventRecord(d.ev0, d.stream));
+            rc = render_tiles(d, cam, p, r, world, dst, d.stream, &launches); if (rc) return rc;
+            if (r == 0) CU(cudaEventRecord(d.ev1, d.stream));
+            if (r != 0) {
+                const size_t bytes = (size_t)rows_of_rank(p->height, p->tile_rows, world, r) * p->width * 4;
+                CU(cudaMemcpyPeerAsync(d0.gathered.p + tile_px * r, d0.device, d.tiles.p, d.device, bytes, d.stream));
+                CU(cudaEventRecord(d.ev_done, d.stream));
+            }
+        }
+        CU(cudaSetDevice(d0.device));
+        for (uint32_t r = 1; r < world; ++r) CU(cudaStreamWaitEvent(d0.stream, c->dev[r].ev_done, 0));
+        const size_t npx = (size_t)p->width * p->height;
+        deinterleave_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, d0.stream>>>(d0.gathered.p, p->width, p->height, p->tile_rows, world, tile_px, d0.frame.p);
+        CU(cudaGetLastError());
+        ++launches;
+        d_final = d0.frame.p;
+    }
+    CU(cudaMemcpyAsync(d0.pinned, d_final, frame_bytes, cudaMemcpyDeviceToHost, d0.stream));
+    CU(cudaMemcpyAsync(d0.pinned_cnt, d0.counters.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d0.stream));
+    CU(cudaStreamSynchronize(d0.stream));
+    memcpy(out_rgba, d0.pinned, frame_bytes);
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        float ms = 0; CU(cudaEventElapsedTime(&ms, d0.ev0, d0.ev1));
+        uint64_t rays = d0.pinned_cnt[1];
+        for (uint32_t r = 1; r < world; ++r) {
+            DeviceState& d = c->dev[r];
+            CU(cudaSetDevice(d.device));
+            CU(cudaMemcpyAsync(d.pinned_cnt, d.counters.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.stream));
+            CU(cudaStreamSynchronize(d.stream));
+            rays += d.pinned_cnt[1];
+        }
+        stats->kernel_ms = ms; stats->total_ms = now_ms() - t0;
+        stats->paths = (uint64_t)p->width * p->height * p->spp;
+        stats->rays_traced = rays; stats->sphere_tests = rays * (uint64_t)d0.scene.n;
+        stats->h2d_bytes = sizeof(rtiow_camera) + sizeof(rtiow_params); stats->d2h_bytes = frame_bytes + 16;
+        stats->kernel_launches = launches; stats->n_gpus = world;
+    }
+    return RTIOW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// unit-level batches
+// ------------------------------------------------------------------------------------------------
+struct Scratch {
+    std::vector<void*> ptrs; cudaStream_t st;
+    explicit Scratch(cudaStream_t s) : st(s) {}
+    ~Scratch() { for (void* p : ptrs) cudaFree(p); }
+    template <typename U> cudaError_t in(const U* host, size_t n, U** dev)
+    {
+        *dev = nullptr;
+        cudaError_t e = cudaMalloc((void**)dev, std::max<size_t>(n, 1) * sizeof(U)); if (e) return e;
+        ptrs.push_back(*dev);
+        if (n) e = cudaMemcpyAsync(*dev, host, n * sizeof(U), cudaMemcpyHostToDevice, st);
+        return e;
+    }
+    template <typename U> cudaError_t out(size_t n, U** dev)
+    {
+        *dev = nullptr;
+        cudaError_t e = cudaMalloc((void**)dev, std::max<size_t>(n, 1) * sizeof(U)); if (e) return e;
+        ptrs.push_back(*dev);
+        return cudaMemsetAsync(*dev, 0, std::max<size_t>(n, 1) * sizeof(U), st);
+    }
+    template <typename U> cudaError_t back(U* host, const U* dev, size_t n) { return n ? cudaMemcpyAsync(host, dev, n * sizeof(U), cudaMemcpyDeviceToHost, st) : cudaSuccess; }
+};
+#define BATCH_PROLOGUE()                                                                     \
+    if (!c) return fail(RTIOW_ERR_INVALID_ARG, "ctx is NULL");                               \
+    if (n < 0) return fail(RTIOW_ERR_INVALID_ARG, "n < 0");                                  \
+    if (precision != RTIOW_PRECISION_F32 && precision != RTIOW_PRECISION_F64) return fail(RTIOW_ERR_INVALID_ARG, "unknown precision"); \
+    DeviceState& d = c->dev[0];                                                              \
+    CU(cudaSetDevice(d.device));                                                             \
+    Scratch S(d.stream);                                                                     \
+    const unsigned grid = (unsigned)((n + 255) / 256);                                       \
+    (void)grid;
+#define N3 ((size_t)n * 3)
+
+extern "C" int rtiow_sphere_hit_batch(rtiow_ctx* c, int precision, int64_t n, const double* center, const double* radius, const double* orig,
+                                      const double* dir, const double* t_min, const double* t_max, int32_t* hit, double* t, double* p,
+                                      double* normal, int32_t* front_face)
+{
+    BATCH_PROLOGUE();
+    if (n == 0) return RTIOW_OK;
+    double *dc, *dr, *dor, *dd, *dtn, *dtx, *dt, *dp, *dn; int32_t *dh, *dff;
+    CU(S.in(center, N3, &dc)); CU(S.in(radius, n, &dr)); CU(S.in(orig, N3, &dor)); CU(S.in(dir, N3, &dd)); CU(S.in(t_min, n, &dtn)); CU(S.in(t_max, n, &dtx));
+    CU(S.out(n, &dh)); CU(S.out(n, &dt)); CU(S.out(N3, &dp)); CU(S.out(N3, &dn)); CU(S.out(n, &dff));
+    if (precision == RTIOW_PRECISION_F64) sphere_hit_kernel<double><<<grid, 256, 0, d.stream>>>(n, dc, dr, dor, dd, dtn, dtx, dh, dt, dp, dn, dff);
+    else sphere_hit_kernel<float><<<grid, 256, 0, d.stream>>>(n, dc, dr, dor, dd, dtn, dtx, dh, dt, dp, dn, dff);
+    CU(cudaGetLastError());
+    CU(S.back(hit, dh, n)); CU(S.back(t, dt, n)); CU(S.back(p, dp, N3)); CU(S.back(normal, dn, N3)); CU(S.back(front_face, dff, n));
+    CU(cudaStreamSynchronize(d.stream));
+    return RTIOW_OK;
+}
+
+extern "C" int rtiow_hitlist_batch(rtiow_ctx* c, int precision, int64_t n, const double* orig, const double* dir, double t_min, int32_t* hit,
+                                   int32_t* index, double* t, double* p, double* normal, int32_t* front_face)
+{
+    BATCH_PROLOGUE();
+    if (!d.has_scene) return fail(RTIOW_ERR_INVALID_ARG, "no scene uploaded");
+    if (n == 0) return RTIOW_OK;
+    double *dor, *dd, *dt, *dp, *dn; int32_t *dh, *di, *dff;
+    CU(S.in(orig, N3, &dor)); CU(S.in(dir, N3, &dd));
+    CU(S.out(n, &dh)); CU(S.out(n, &di)); CU(S.out(n, &dt)); CU(S.out(N3, &dp)); CU(S.out(N3, &dn)); CU(S.out(n, &dff));
+    if (precision == RTIOW_PRECISION_F64) {
+        hitlist_kernel<double, false, 256><<<grid, 256, 0, d.stream>>>(d.scene, n, dor, dd, t_min, dh, di, dt, dp, dn, dff);
+    } else {
+        const ScanCfg cfg = pick_cfg(d.scene.np);
+        if (cfg.variant == 0) {
+            hitlist_kernel<float, true, 256><<<grid, 256, cfg.smem, d.stream>>>(d.scene, n, dor, dd, t_min, dh, di, dt, dp, dn, dff);
+        } else if (cfg.variant == 1) {
+            auto k = hitlist_kernel<float, true, 512>;
+            CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+            k<<<(unsigned)((n + 511) / 512), 512, cfg.smem, d.stream>>>(d.scene, n, dor, dd, t_min, dh, di, dt, dp, dn, dff);
+        } else {
+            hitlist_kernel<float, false, 256><<<grid, 256, cfg.smem, d.stream>>>(d.scene, n, dor, dd, t_min, dh, di, dt, dp, dn, dff);
+        }
+    }
+    CU(cudaGetLastError());
+    CU(S.back(hit, dh, n)); CU(S.back(index, di, n)); CU(S.back(t, dt, n)); CU(S.back(p, dp, N3)); CU(S.back(normal, dn, N3)); CU(S.back(front_face, dff, n));
+    CU(cudaStreamSynchronize(d.stream));
+    return RTIOW_OK;
+}
+
+extern "C" int rtiow_scatter_batch(rtiow_ctx* c, int precision, int64_t n, const int32_t* kind, const double* albedo, const double* param,
+                                   const double* r_orig, const double* r_dir, const double* p, const double* normal, const int32_t* front_face,
+                                   const double* sample, int32_t* some, double* attenuation, double* s_orig, double* s_dir)
+{
+    BATCH_PROLOGUE();
+    if (n == 0) return RTIOW_OK;
+    for (int64_t i = 0; i < n; ++i) if (kind[i] < 0 || kind[i] > RTIOW_MAT_DIELECTRIC) return fail(RTIOW_ERR_UNSUPPORTED, "item %lld: material kind %d", (long long)i, kind[i]);
+    int32_t *dk, *dff, *dsome; double *da, *dpar, *dro, *drd, *dp, *dn, *dsm, *datt, *dso, *dsd;
+    CU(S.in(kind, n, &dk)); CU(S.in(albedo, N3, &da)); CU(S.in(param, n, &dpar)); CU(S.in(r_orig, N3, &dro)); CU(S.in(r_dir, N3, &drd));
+    CU(S.in(p, N3, &dp)); CU(S.in(normal, N3, &dn)); CU(S.in(front_face, n, &dff)); CU(S.in(sample, N3, &dsm));
+    CU(S.out(n, &dsome)); CU(S.out(N3, &datt)); CU(S.out(N3, &dso)); CU(S.out(N3, &dsd));
+    if (precision == RTIOW_PRECISION_F64) scatter_kernel<double><<<grid, 256, 0, d.stream>>>(n, dk, da, dpar, dro, drd, dp, dn, dff, dsm, dsome, datt, dso, dsd);
+    else scatter_kernel<float><<<grid, 256, 0, d.stream>>>(n, dk, da, dpar, dro, drd, dp, dn, dff, dsm, dsome, datt, dso, dsd);
+    CU(cudaGetLastError());
+    CU(S.back(some, dsome, n)); CU(S.back(attenuation, datt, N3)); CU(S.back(s_orig, dso, N3)); CU(S.back(s_dir, dsd, N3));
+    CU(cudaStreamSynchronize(d.stream));
+    return RTIOW_OK;
+}
+
+extern "C" int rtiow_get_ray_batch(rtiow_ctx* c, int precision, const rtiow_camera* cam, int64_t n, const double* s, const double* t,
+                                   const double* disk_xy, double* orig, double* dir)
+{
+    BATCH_PROLOGUE();
+    if (!cam) return fail(RTIOW_ERR_INVALID_ARG, "cam is NULL");
+    if (n == 0) return RTIOW_OK;
+    double *ds, *dt, *dk, *dor, *dd;
+    CU(S.in(s, n, &ds)); CU(S.in(t, n, &dt)); CU(S.in(disk_xy, (size_t)n * 2, &dk)); CU(S.out(N3, &dor)); CU(S.out(N3, &dd));
+    if (precision == RTIOW_PRECISION_F64) get_ray_kernel<double><<<grid, 256, 0, d.stream>>>(to_dev_camera<double>(*cam), n, ds, dt, dk, dor, dd);
+    else get_ray_kernel<float><<<grid, 256, 0, d.stream>>>(to_dev_camera<float>(*cam), n, ds, dt, dk, dor, dd);
+    CU(cudaGetLastError());
+    CU(S.back(orig, dor, N3)); CU(S.back(dir, dd, N3));
+    CU(cudaStreamSynchronize(d.stream));
+    return RTIOW_OK;
+}
+
+extern "C" int rtiow_to_rgba_batch(rtiow_ctx* c, int precision, int64_t n, const double* color, uint8_t alpha, uint64_t spp, uint8_t* out_rgba)
+{
+    BATCH_PROLOGUE();
+    if (spp == 0) return fail(RTIOW_ERR_INVALID_ARG, "spp must be >= 1");
+    if (n == 0) return RTIOW_OK;
+    double* dc; uint32_t* dout;
+    CU(S.in(color, N3, &dc)); CU(S.out(n, &dout));
+    if (precision == RTIOW_PRECISION_F64) to_rgba_kernel<double><<<grid, 256, 0, d.stream>>>(n, dc, alpha, spp, dout);
+    else to_rgba_kernel<float><<<grid, 256, 0, d.stream>>>(n, dc, alpha, spp, dout);
+    CU(cudaGetLastError());
+    CU(S.back((uint32_t*)out_rgba, dout, n));
+    CU(cudaStreamSynchronize(d.stream));
+    return RTIOW_OK;
+}
+
+extern "C" int rtiow_reflect_batch(rtiow_ctx* c, int precision, int64_t n, const double* v, const double* nrm, double* out)
+{
+    BATCH_PROLOGUE();
+    if (n == 0) return RTIOW_OK;
+    double *dv, *dn, *dout;
+    CU(S.in(v, N3, &dv)); CU(S.in(nrm, N3, &dn)); CU(S.out(N3, &dout));
+    if (precision == RTIOW_PRECISION_F64) reflect_kernel<double><<<grid, 256, 0, d.stream>>>(n, dv, dn, dout);
+    else reflect_kernel<float><<<grid, 256, 0, d.stream>>>(n, dv, dn, dout);
+    CU(cudaGetLastError());
+    CU(S.back(out, dout, N3));
+    CU(cudaStreamSynchronize(d.stream));
+    return RTIOW_OK;
+}
+
+extern "C" int rtiow_refract_batch(rtiow_ctx* c, int precision, int64_t n, const double* uv, const double* nrm, const double* eta, double* out)
+{
+    BATCH_PROLOGUE();
+    if (n == 0) return RTIOW_OK;
+    double *dv, *dn, *de, *dout;
+    CU(S.in(uv, N3, &dv)); CU(S.in(nrm, N3, &dn)); CU(S.in(eta, n, &de)); CU(S.out(N3, &dout));
+    if (precision == RTIOW_PRECISION_F64) refract_kernel<double><<<grid, 256, 0, d.stream>>>(n, dv, dn, de, dout);
+    else refract_kernel<float><<<grid, 256, 0, d.stream>>>(n, dv, dn, de, dout);
+    CU(cudaGetLastError());
+    CU(S.back(out, dout, N3));
+    CU(cudaStreamSynchronize(d.stream));
+    return RTIOW_OK;
+}
+
+extern "C" int rtiow_ray_color_batch(rtiow_ctx* c, int precision, int64_t n, const double* orig, const double* dir, const uint32_t* pixel,
+                                     const uint32_t* sample, uint64_t seed, int32_t max_depth, double t_min, double* color, uint64_t* rays)
+{
+    BATCH_PROLOGUE();
+    if (!d.has_scene) return fail(RTIOW_ERR_INVALID_ARG, "no scene uploaded");
+    if (n == 0) return RTIOW_OK;
+    double *dor, *dd, *dcol; uint32_t *dpx, *dsm; unsigned long long* dr;
+    CU(S.in(orig, N3, &dor)); CU(S.in(dir, N3, &dd)); CU(S.in(pixel, n, &dpx)); CU(S.in(sample, n, &dsm));
+    CU(S.out(N3, &dcol)); CU(S.out(n, &dr));
+    if (precision == RTIOW_PRECISION_F64) {
+        ray_color_kernel<double, false, 256><<<grid, 256, 0, d.stream>>>(d.scene, n, dor, dd, dpx, dsm, seed, max_depth, t_min, dcol, dr);
+    } else {
+        const ScanCfg cfg = pick_cfg(d.scene.np);
+        if (cfg.variant == 0) {
+            ray_color_kernel<float, true, 256><<<grid, 256, cfg.smem, d.stream>>>(d.scene, n, dor, dd, dpx, dsm, seed, max_depth, t_min, dcol, dr);
+        } else if (cfg.variant == 1) {
+            auto k = ray_color_kernel<float, true, 512>;
+            CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+            k<<<(unsigned)((n + 511) / 512), 512, cfg.smem, d.stream>>>(d.scene, n, dor, dd, dpx, dsm, seed, max_depth, t_min, dcol, dr);
+        } else {
+            ray_color_kernel<float, false, 256><<<grid, 256, cfg.smem, d.stream>>>(d.scene, n, dor, dd, dpx, dsm, seed, max_depth, t_min, dcol, dr);
+        }
+    }
+    CU(cudaGetLastError());
+    CU(S.back(color, dcol, N3));
+    if (rays) CU(S.back((unsigned long long*)rays, dr, n));
+    CU(cudaStreamSynchronize(d.stream));
+    return RTIOW_OK;
+}
+
+extern "C" int rtiow_sampler_batch(rtiow_ctx* c, int precision, int64_t n, const uint32_t* pixel, const uint32_t* sample, const uint32_t* bounce,
+                                   uint64_t seed, double* out)
+{
+    BATCH_PROLOGUE();
+    if (n == 0) return RTIOW_OK;
+    uint32_t *dp, *ds, *db; double* dout;
+    CU(S.in(pixel, n, &dp)); CU(S.in(sample, n, &ds)); CU(S.in(bounce, n, &db)); CU(S.out((size_t)n * 12, &dout));
+    if (precision == RTIOW_PRECISION_F64) sampler_kernel<double><<<grid, 256, 0, d.stream>>>(n, dp, ds, db, seed, dout);
+    else sampler_kernel<float><<<grid, 256, 0, d.stream>>>(n, dp, ds, db, seed, dout);
+    CU(cudaGetLastError());
+    CU(S.back(out, dout, (size_t)n * 12));
+    CU(cudaStreamSynchronize(d.stream));
+    return RTIOW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// measurement helpers
+// ------------------------------------------------------------------------------------------------
+extern "C" int rtiow_fp32_peak_probe(rtiow_ctx* c, int packed, double target_ms, double* out_tflops, double* out_ms)
+{
+    if (!c || !out_tflops) return fail(RTIOW_ERR_INVALID_ARG, "NULL argument");
+    DeviceState& d = c->dev[0];
+    CU(cudaSetDevice(d.device));
+    const int threads = 256, ctas = d.sms * 8;
+    CU(d.probe.resize((size_t)threads * ctas));
+    auto run = [&](int iters) -> cudaError_t {
+        if (packed) probe_ffma2_kernel<<<ctas, threads, 0, d.stream>>>(d.probe.p, iters, 1.0001f, 0.5f);
+        else probe_ffma_kernel<<<ctas, threads, 0, d.stream>>>(d.probe.p, iters, 1.0001f, 0.5f);
+        return cudaGetLastError();
+    };
+    const double flop_per_iter = (packed ? 4.0 : 2.0) * 64.0 * threads * ctas;
+    CU(run(256)); CU(cudaStreamSynchronize(d.stream));
+    CU(cudaEventRecord(d.ev0, d.stream)); CU(run(2048)); CU(cudaEventRecord(d.ev1, d.stream)); CU(cudaStreamSynchronize(d.stream));
+    float ms = 0; CU(cudaEventElapsedTime(&ms, d.ev0, d.ev1));
+    double want = target_ms > 0 ? target_ms : 50.0;
+    long long iters = (long long)(2048.0 * want / std::max(ms, 1e-3f));
+    iters = std::max<long long>(2048, std::min<long long>(iters, 1LL << 30));
+    CU(cudaEventRecord(d.ev0, d.stream)); CU(run((int)iters)); CU(cudaEventRecord(d.ev1, d.stream)); CU(cudaStreamSynchronize(d.stream));
+    CU(cudaEventElapsedTime(&ms, d.ev0, d.ev1));
+    *out_tflops = flop_per_iter * (double)iters / (ms * 1e-3) * 1e-12;
+    if (out_ms) *out_ms = ms;
+    return RTIOW_OK;
+}
+
+extern "C" int rtiow_flush_l2(rtiow_ctx* c)
+{
+    if (!c) return fail(RTIOW_ERR_INVALID_ARG, "ctx is NULL");
+    for (auto& d : c->dev) {
+        CU(cudaSetDevice(d.device));
+        const size_t n = (size_t)256 * 1024 * 1024 / sizeof(uint4);     // 256 MiB > the 126 MB L2
+        CU(d.flush.resize(n));
+        flush_kernel<<<d.sms * 8, 256, 0, d.stream>>>(d.flush.p, n, 0x5a5a5a5au);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(d.stream));
+    }
+    return RTIOW_OK;
+}

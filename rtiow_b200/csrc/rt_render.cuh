@@ -1,0 +1,221 @@
+// rt_render.cuh — the render megakernel: the pixel/sample loop (main.rs:122-139), ray_color
+// (main.rs:38-57) as an iterative bounce loop, and the quantise + row flip (main.rs:137,141-145).
+//
+// Execution model (B200, 148 SMs): a persistent grid of kCtasPerSm x SM-count CTAs.  Every lane owns
+// one PATH at a time; when its path ends (miss -> sky, absorbed, depth exhausted) the lane pulls the
+// next (pixel, sample) from its warp's chunk, so the sphere scan — >95 % of the work — always runs
+// with 32 live lanes regardless of the heavy-tailed path length (1..max_depth rays).
+// Sample radiance is accumulated in 32.32 fixed point (integer adds are associative), so the
+// image is bit-identical for any chunk size, grid size or GPU count.
+#pragma once
+#include "rt_scene.cuh"
+
+namespace rt {
+
+template <typename T> struct RenderArgs {
+    SceneDev scene;
+    CameraT<T> cam;
+    uint32_t width, height, spp;
+    int32_t max_depth;
+    T t_min;
+    uint64_t seed;
+    // frame partition: this launch renders rows {y : (y / tile_rows) % world == rank}
+    uint32_t rank, world, tile_rows, local_rows;
+    uint32_t chunk_samples;        // samples per chunk (<= spp); chunks never straddle pixels
+    uint32_t chunks_per_pixel;
+    uint32_t chunks_per_fetch;
+    uint64_t n_chunks;
+    unsigned long long* accum;     // [3][local_rows*width] 32.32 fixed-point radiance sums
+    unsigned long long* work_counter;
+    unsigned long long* ray_counter;
+    int np_smem;                   // 1: filter SoA staged in shared memory
+};
+
+#define RT_FIX_SCALE 4294967296.0f   // 2^32
+
+__device__ __forceinline__ unsigned long long to_fix(float c)
+{
+    // NaN/negative -> 0, saturating: a poisoned sample contributes nothing (the reference would
+    // turn the whole pixel black through NaN -> `as u8` = 0, vec3.rs:415-417; measure-zero event)
+    return __float2ull_rn(fminf(fmaxf(c, 0.0f), 1.0e9f) * RT_FIX_SCALE);
+}
+__device__ __forceinline__ unsigned long long to_fix(double c)
+{
+    return __double2ull_rn(fmin(fmax(c, 0.0), 1.0e9) * 4294967296.0);
+}
+
+// local row -> global top-down row under the interleaved-tile partition
+__device__ __forceinline__ uint32_t local_to_global_row(uint32_t lr, uint32_t tile_rows, uint32_t world, uint32_t rank)
+{
+    const uint32_t tl = lr / tile_rows, within = lr - tl * tile_rows;
+    return (tl * world + rank) * tile_rows + within;
+}
+
+template <typename T, bool kSmem, int kThreads, int kMinCtas>
+__global__ void __launch_bounds__(kThreads, kMinCtas) render_kernel(const RenderArgs<T> a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* s_soa = reinterpret_cast<float*>(smem_raw);
+    const int np = a.scene.np;
+    const float* soa = a.scene.soa;
+    uint16_t* cand_base;
+    if (kSmem) {
+        stage_scene(s_soa, a.scene.soa, np);
+        soa = s_soa;
+        cand_base = reinterpret_cast<uint16_t*>(s_soa + 4 * (size_t)np);
+    } else {
+        cand_base = reinterpret_cast<uint16_t*>(smem_raw);
+    }
+    uint16_t* cand = cand_base + threadIdx.x;          // slot k of this lane at cand[k * kThreads]
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    // ---- per-lane path state ----------------------------------------------------------------
+    bool active = false;
+    V3<T> o = mk<T>(0, 0, 0), dhat = mk<T>(0, 1, 0), thr = mk<T>(0, 0, 0);
+    T tmin_n = T(0);
+    uint32_t pix_key = 0, smp = 0, bounce = 0;
+    int depth = 0;
+    uint32_t acc_lp = 0xffffffffu;                      // local pixel the accumulators belong to
+    unsigned long long acc_r = 0, acc_g = 0, acc_b = 0;
+    uint32_t n_rays = 0;
+    // ---- warp-uniform work cursor ---------------------------------------------------------------
+    uint32_t cs = 0, ce = 0, c_lp = 0, c_x = 0, c_y = 0;
+    unsigned long long cc = 0, cce = 0;
+    bool exhausted = false;
+    const uint32_t n_lp_stride = a.local_rows * a.width;
+
+    for (;;) {
+        // ---- regeneration: idle lanes start the next path (main.rs:130-134) ------------------------
+        unsigned need = __ballot_sync(RT_FULL, !active);
+        while (need && !exhausted) {
+            if (cs == ce) {
+                if (cc == cce) {
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(a.work_counter, (unsigned long long)a.chunks_per_fetch);
+                    cc = __shfl_sync(RT_FULL, base, 0);
+                    cce = cc + a.chunks_per_fetch; if (cce > a.n_chunks) cce = a.n_chunks;
+                    if (cc >= a.n_chunks) { exhausted = true; break; }
+                }
+                const unsigned long long c = cc++;
+                c_lp = (uint32_t)(c / a.chunks_per_pixel);
+                const uint32_t part = (uint32_t)(c - (unsigned long long)c_lp * a.chunks_per_pixel);
+                cs = part * a.chunk_samples; ce = min(cs + a.chunk_samples, a.spp);
+                const uint32_t lr = c_lp / a.width;
+                c_x = c_lp - lr * a.width;
+                c_y = local_to_global_row(lr, a.tile_rows, a.world, a.rank);
+            }
+            const uint32_t avail = ce - cs;
+            const uint32_t r = __popc(need & lt_mask);
+            if (!active && r < avail) {
+                if (acc_lp != c_lp) {                   // flush the previous pixel's partial sums
+                    if (acc_lp != 0xffffffffu) {
+                        atomicAdd(a.accum + acc_lp, acc_r);
+                        atomicAdd(a.accum + n_lp_stride + acc_lp, acc_g);
+                        atomicAdd(a.accum + 2 * (size_t)n_lp_stride + acc_lp, acc_b);
+                    }
+                    acc_lp = c_lp; acc_r = acc_g = acc_b = 0;
+                }
+                smp = cs + r;
+                const uint32_t j = a.height - 1u - c_y;                 // j = 0 is the bottom row (main.rs:132,141-145)
+                pix_key = j * a.width + c_x;
+                const Uniform4<T> u = event_uniforms<T>(a.seed, pix_key, smp, 0u);
+                const T su = (T(c_x) + u.u0) / T(a.width - 1u);         // main.rs:131
+                const T sv = (T(j) + u.u1) / T(a.height - 1u);          // main.rs:132
+                T dx, dy; direct_disk(u.u2, u.u3, &dx, &dy);            // camera.rs:48
+                V3<T> d; get_ray(a.cam, su, sv, dx, dy, &o, &d);        // main.rs:134
+                const T len = length(d);
+                dhat = d * (T(1) / len);
+                tmin_n = a.t_min * len;                                 // t is measured in |dir| units (Appendix C.3)
+                thr = mk<T>(1, 1, 1);
+                depth = a.max_depth; bounce = 0;
+                active = depth > 0;                                      // main.rs:40-42
+            }
+            cs += min((uint32_t)__popc(need), avail);
+            need = __ballot_sync(RT_FULL, !active);
+        }
+        if (!__any_sync(RT_FULL, active)) break;
+
+        // ---- world.hit(r, t_min, INFINITY) (main.rs:44): all 32 lanes scan together ----------------
+        T t_hit; int idx;
+        if (sizeof(T) == 4) {
+            HitF h = closest_hit<kSmem>(a.scene, soa, mk<float>((float)o.x, (float)o.y, (float)o.z),
+                                        mk<float>((float)dhat.x, (float)dhat.y, (float)dhat.z), (float)tmin_n, cand, kThreads);
+            t_hit = (T)h.t; idx = h.idx;
+        } else {
+            double td; closest_hit_f64(a.scene, mk<double>(o.x, o.y, o.z), mk<double>(dhat.x, dhat.y, dhat.z), (double)tmin_n, &td, &idx);
+            t_hit = (T)td;
+        }
+
+        if (active) {
+            ++n_rays;
+            if (idx < 0) {                                               // miss: sky (main.rs:54-56)
+                const V3<T> c = thr * sky(dhat);
+                acc_r += to_fix(c.x); acc_g += to_fix(c.y); acc_b += to_fix(c.z);
+                active = false;
+            } else {
+                V3<T> cen; T rad; V3<T> albedo; T param;
+                if (sizeof(T) == 4) {
+                    const float4 s = a.scene.sph[idx], m = a.scene.mat[idx];
+                    cen = mk<T>(s.x, s.y, s.z); rad = s.w; albedo = mk<T>(m.x, m.y, m.z); param = m.w;
+                } else {
+                    const double4 s = a.scene.sphd[idx], m = a.scene.matd[idx];
+                    cen = mk<T>(s.x, s.y, s.z); rad = s.w; albedo = mk<T>(m.x, m.y, m.z); param = m.w;
+                }
+                const int kind = a.scene.kind[idx];
+                const V3<T> p = o + dhat * t_hit;                        // ray.rs:15-17
+                V3<T> n; bool ff; hit_record(p, cen, rad, dhat, &n, &ff);  // sphere.rs:36-39
+                ++bounce;
+                const Uniform4<T> u = event_uniforms<T>(a.seed, pix_key, smp, bounce);
+                V3<T> sample;
+                if (kind == MAT_LAMBERTIAN) sample = direct_unit_vector(u.u0, u.u1);
+                else if (kind == MAT_METAL) sample = direct_in_unit_sphere(u.u0, u.u1, u.u2);
+                else sample = mk<T>(u.u0, 0, 0);
+                V3<T> att, nd;
+                const bool some = scatter(kind, albedo, param, dhat, n, ff, sample, &att, &nd);   // main.rs:47
+                --depth;
+                if (!some || depth <= 0) {                                // main.rs:51 / main.rs:40-42: black
+                    active = false;
+                } else {
+                    thr = thr * att;                                      // main.rs:49 as a running product
+                    const T len = length(nd);
+                    o = p; dhat = nd * (T(1) / len); tmin_n = a.t_min * len;
+                }
+            }
+        }
+    }
+    if (acc_lp != 0xffffffffu) {
+        atomicAdd(a.accum + acc_lp, acc_r);
+        atomicAdd(a.accum + n_lp_stride + acc_lp, acc_g);
+        atomicAdd(a.accum + 2 * (size_t)n_lp_stride + acc_lp, acc_b);
+    }
+    // rays traced by this warp -> one atomic (world.hit call count, main.rs:44)
+    uint32_t wr = __reduce_add_sync(RT_FULL, n_rays);
+    if (lane == 0) atomicAdd(a.ray_counter, (unsigned long long)wr);
+}
+
+// Color::to_rgba (vec3.rs:404-420) + the row flip (main.rs:141-145): fixed-point sums -> top-down
+// RGBA8 rows of this rank's tile buffer (rank-local row order).
+__global__ void finalize_kernel(const unsigned long long* __restrict__ accum, uint32_t n_lp, uint32_t spp, uint32_t alpha,
+                                uint32_t* __restrict__ out_rgba)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_lp) return;
+    const double k = 1.0 / 4294967296.0;
+    const V3<double> sum = mk<double>((double)accum[i] * k, (double)accum[n_lp + i] * k, (double)accum[2 * (size_t)n_lp + i] * k);
+    out_rgba[i] = to_rgba<double>(sum, alpha, (uint64_t)spp);
+}
+
+// gathered tile buffers (rank-major, rank-local rows) -> top-down frame
+__global__ void deinterleave_kernel(const uint32_t* __restrict__ gathered, uint32_t width, uint32_t height, uint32_t tile_rows,
+                                    uint32_t world, size_t tile_buf_pixels, uint32_t* __restrict__ frame)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)width * height) return;
+    const uint32_t y = (uint32_t)(i / width), x = (uint32_t)(i - (size_t)y * width);
+    const uint32_t tg = y / tile_rows, within = y - tg * tile_rows;
+    const uint32_t rank = tg % world, lr = (tg / world) * tile_rows + within;
+    frame[i] = gathered[rank * tile_buf_pixels + (size_t)lr * width + x];
+}
+
+}  // namespace rt

@@ -1,0 +1,176 @@
+// rt_scene.cuh — device-resident scene layout and the closest-hit scan (HittableList::hit,
+// /root/reference/src/shapes/mod.rs:56-69) of the B200 render path.
+//
+// Layout in HBM (built once by rtiow_scene_upload, read-only afterwards):
+//   soa      float [4][np]   cx | cy | cz | r2f   "small" spheres in list order, padded to a multiple
+//                            of 32 with never-hit entries; staged into shared memory by each CTA and
+//                            streamed as broadcast LDS.128 (4 spheres per load per array)
+//   small    float4 [np]     (cx, cy, cz, r) exact f32 copy for the precise test of candidates
+//   small_idx int   [np]     position in `small` -> index in the reference's list (-1 = padding)
+//   big      double4 [nb]    (cx, cy, cz, r) spheres whose radius makes |oc|^2 - r^2 cancel in f32
+//                            (the r=1000 ground, main.rs:64); tested in f64, 1 of ~530 tests
+//   big_idx  int    [nb]
+//   sph      float4 / double4 [n]  (cx,cy,cz,r) in list order, for HitRecord::new
+//   mat      float4 / double4 [n]  (albedo r,g,b, fuzz|ir) resolved per sphere; kind uint8 [n]
+#pragma once
+#include "rt_device.cuh"
+
+namespace rt {
+
+struct SceneDev {
+    const float* soa;
+    const float4* small;
+    const int* small_idx;
+    int np;
+    const double4* big;
+    const int* big_idx;
+    int nb;
+    const float4* sph;
+    const double4* sphd;
+    const float4* mat;
+    const double4* matd;
+    const uint8_t* kind;
+    int n;
+};
+
+#define RT_FULL 0xffffffffu
+// d' = d * (1 + 2^-21): the filter sees half_b^2 inflated by ~2^-20, four times the worst-case f32
+// rounding of the filter expression, so every sphere the precise test can accept passes the filter.
+#define RT_FILTER_DIR_SCALE 1.000000476837158203125f
+#define RT_CAND_CAP 16           // candidate slots per lane per segment (uint16 positions)
+#define RT_SEG_WORDS 32          // 32 words x 32 spheres per segment between drains
+
+struct HitF {           // closest hit so far; t in units of the normalised direction
+    float t;
+    int idx;            // index in the reference's list, -1 = none
+};
+
+// Precise test of one candidate (sphere.rs:16-34 via sphere_roots), index-aware acceptance.
+// The reference scans in list order and accepts root <= closest_so_far, so among equal roots the
+// LARGEST index wins (sphere.rs:29,31; mod.rs:61-66); `t < best || (t == best && idx > best_idx)`
+// gives the same winner for any processing order.
+template <typename T>
+__device__ __forceinline__ void candidate(V3<T> o, V3<T> dhat, T inv_a, T t_min, V3<T> c, T r, int idx, T* t_best, int* i_best)
+{
+    T t;
+    // t_max = +inf: a root beyond the current closest is rejected by the comparison below, exactly
+    // as sphere.rs:29-33 rejects it (its far root is farther still)
+    if (!sphere_roots(c - o, dhat, inv_a, r * r, t_min, (T)__int_as_float(0x7f800000), &t)) return;
+    if (t < *t_best || (t == *t_best && idx > *i_best)) { *t_best = t; *i_best = idx; }
+}
+
+// The f32 scan over the shared-memory SoA.
+//   filter (all spheres, branch-free, packed f32x2 over sphere pairs):
+//       oc = c - o;  hb = oc . d';  disc' = hb^2 - |oc|^2 + r2f        (10 packed ops per 2 tests)
+//     disc' >= 0 is a conservative superset of "discriminant >= 0" (sphere.rs:24-25); its sign bit is
+//     funnel-shifted into a 32-sphere word (1 SHF per test on the ALU pipe, co-issued).
+//   candidates (a few per ray): positions appended to a per-lane list in shared memory, then the
+//     whole warp drains its lists in lock-step through candidate<float>.
+// s_soa: [4][np] floats in shared memory (or global when the scene does not fit).
+template <bool kSmem>
+__device__ __forceinline__ void scan_small(const float* __restrict__ s_soa, int np, const float4* __restrict__ small,
+                                           V3<float> o, V3<float> dhat, float inv_a, float t_min,
+                                           uint16_t* cand, int cand_stride, float* t_best, int* p_best)
+{
+    const int n4 = np >> 2;
+    const float4* CX = reinterpret_cast<const float4*>(s_soa);
+    const float4* CY = CX + n4;
+    const float4* CZ = CY + n4;
+    const float4* RR = CZ + n4;
+    const float2 OX = bc2(o.x), OY = bc2(o.y), OZ = bc2(o.z);
+    const float2 DX = bc2(dhat.x * RT_FILTER_DIR_SCALE), DY = bc2(dhat.y * RT_FILTER_DIR_SCALE), DZ = bc2(dhat.z * RT_FILTER_DIR_SCALE);
+    const int n_words = np >> 5;
+    int pb = *p_best; float tb = *t_best;
+
+    for (int w0 = 0; w0 < n_words; w0 += RT_SEG_WORDS) {
+        const int w1 = min(w0 + RT_SEG_WORDS, n_words);
+        int nc = 0;
+        for (int w = w0; w < w1; ++w) {
+            unsigned m = 0;
+            const int q0 = w << 3;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 cx = CX[q0 + q], cy = CY[q0 + q], cz = CZ[q0 + q], rr = RR[q0 + q];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const float2 X = h ? make_float2(cx.z, cx.w) : make_float2(cx.x, cx.y);
+                    const float2 Y = h ? make_float2(cy.z, cy.w) : make_float2(cy.x, cy.y);
+                    const float2 Z = h ? make_float2(cz.z, cz.w) : make_float2(cz.x, cz.y);
+                    const float2 Q = h ? make_float2(rr.z, rr.w) : make_float2(rr.x, rr.y);
+                    const float2 ocx = fsub2(X, OX), ocy = fsub2(Y, OY), ocz = fsub2(Z, OZ);
+                    const float2 hb = ffma2(ocz, DZ, ffma2(ocy, DY, fmul2(ocx, DX)));
+                    const float2 nc2 = ffma2(neg2(ocx), ocx, ffma2(neg2(ocy), ocy, ffma2(neg2(ocz), ocz, Q)));
+                    const float2 disc = ffma2(hb, hb, nc2);
+                    m = __funnelshift_l(__float_as_uint(disc.x), m, 1);
+                    m = __funnelshift_l(__float_as_uint(disc.y), m, 1);
+                }
+            }
+            unsigned c = ~m;                         // bit (31-k) set: sphere 32w+k passed the filter
+            while (c) {
+                const int k = __clz(c);
+                c &= ~(0x80000000u >> k);
+                const int p = (w << 5) + k;
+                if (nc < RT_CAND_CAP) { cand[nc * cand_stride] = (uint16_t)(p - (w0 << 5)); ++nc; }
+                else { const float4 s = small[p]; candidate<float>(o, dhat, inv_a, t_min, mk(s.x, s.y, s.z), s.w, p, &tb, &pb); }
+            }
+        }
+        const int nmax = __reduce_max_sync(RT_FULL, nc);
+        for (int k = 0; k < nmax; ++k) {
+            if (k < nc) {
+                const int p = (w0 << 5) + cand[k * cand_stride];
+                const float4 s = small[p];
+                candidate<float>(o, dhat, inv_a, t_min, mk(s.x, s.y, s.z), s.w, p, &tb, &pb);
+            }
+        }
+    }
+    *p_best = pb; *t_best = tb;
+}
+
+// Closest hit of one ray against the whole scene: HittableList::hit (mod.rs:56-69).
+// float: packed filter over the small spheres + f64 test of the big ones; all lanes of the warp
+// must call together.  Returns t in dhat units and the list index (or -1).
+template <bool kSmem>
+__device__ __forceinline__ HitF closest_hit(const SceneDev& sc, const float* s_soa, V3<float> o, V3<float> dhat, float t_min,
+                                            uint16_t* cand, int cand_stride)
+{
+    const float inv_a = 1.0f / length_squared(dhat);
+    float tb = __int_as_float(0x7f800000);   // f64::INFINITY at main.rs:44
+    int pb = -1;
+    scan_small<kSmem>(s_soa, sc.np, sc.small, o, dhat, inv_a, t_min, cand, cand_stride, &tb, &pb);
+    HitF h; h.t = tb; h.idx = pb >= 0 ? sc.small_idx[pb] : -1;
+    if (sc.nb > 0) {
+        const V3<double> od = mk<double>(o.x, o.y, o.z), dd = mk<double>(dhat.x, dhat.y, dhat.z);
+        const double inv_ad = 1.0 / length_squared(dd);
+        double tbd = (double)h.t; int ib = h.idx;
+        for (int b = 0; b < sc.nb; ++b) {
+            const double4 s = sc.big[b];
+            candidate<double>(od, dd, inv_ad, (double)t_min, mk(s.x, s.y, s.z), s.w, sc.big_idx[b], &tbd, &ib);
+        }
+        if (ib != h.idx) { h.idx = ib; h.t = (float)tbd; }
+    }
+    return h;
+}
+
+// double: the reference's arithmetic width, every sphere through the precise test (triage mode).
+__device__ __forceinline__ void closest_hit_f64(const SceneDev& sc, V3<double> o, V3<double> dhat, double t_min, double* t_out, int* idx_out)
+{
+    const double inv_a = 1.0 / length_squared(dhat);
+    double tb = __longlong_as_double(0x7ff0000000000000LL);
+    int ib = -1;
+    for (int i = 0; i < sc.n; ++i) {
+        const double4 s = sc.sphd[i];
+        candidate<double>(o, dhat, inv_a, t_min, mk(s.x, s.y, s.z), s.w, i, &tb, &ib);
+    }
+    *t_out = tb; *idx_out = ib;
+}
+
+// cooperative copy of the filter SoA into shared memory (16-byte vector copies; np % 32 == 0)
+__device__ __forceinline__ void stage_scene(float* s_soa, const float* __restrict__ g_soa, int np)
+{
+    const float4* src = reinterpret_cast<const float4*>(g_soa);
+    float4* dst = reinterpret_cast<float4*>(s_soa);
+    for (int i = threadIdx.x; i < np; i += blockDim.x) dst[i] = src[i];   // 4*np floats = np float4
+    __syncthreads();
+}
+
+}  // namespace rt
