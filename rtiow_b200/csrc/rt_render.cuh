@@ -51,6 +51,80 @@ __device__ __forceinline__ uint32_t local_to_global_row(uint32_t lr, uint32_t ti
     return (tl * world + rank) * tile_rows + within;
 }
 
+// One path in flight (one lane).  The ray is (o, dhat) with |dir| folded into tmin_n; self_* name the
+// sphere the ray starts on (rt_scene.cuh, candidate_self).
+template <typename T> struct PathState {
+    V3<T> o, dhat, thr, self_n;
+    T tmin_n;
+    int self_code;
+    uint32_t pix_key, smp, bounce;
+    int depth;
+};
+
+template <typename T> __device__ __forceinline__ void start_ray(PathState<T>& ps, V3<T> orig, V3<T> dir, T t_min)
+{
+    const T len = length(dir);
+    ps.o = orig; ps.dhat = dir * (T(1) / len);
+    ps.tmin_n = t_min * len;                        // t is measured in |dir| units (Appendix C.3)
+}
+
+// One iteration of ray_color (main.rs:38-57) for every lane of the warp: world.hit, then the miss /
+// scatter / absorb branches.  Lanes with active == false still take part in the scan (its warp-level
+// operations need all 32) but ignore the result.  Returns the lane's new `active`; when the path ends,
+// *radiance receives its value (throughput x sky, or black).
+template <typename T, bool kSmem>
+__device__ __forceinline__ bool bounce_step(const SceneDev& sc, const float* soa, uint16_t* cand, int cand_stride, uint64_t seed, T t_min,
+                                            bool active, PathState<T>& ps, V3<T>* radiance, uint32_t* n_rays)
+{
+    T t_hit; int idx, code;
+    if (sizeof(T) == 4) {                                                     // world.hit(r, t_min, INFINITY), main.rs:44
+        const HitF h = closest_hit<kSmem>(sc, soa, mk<float>((float)ps.o.x, (float)ps.o.y, (float)ps.o.z),
+                                          mk<float>((float)ps.dhat.x, (float)ps.dhat.y, (float)ps.dhat.z), (float)ps.tmin_n, ps.self_code,
+                                          mk<float>((float)ps.self_n.x, (float)ps.self_n.y, (float)ps.self_n.z), cand, cand_stride);
+        t_hit = (T)h.t; idx = h.idx; code = h.code;
+    } else {
+        double td;
+        closest_hit_f64(sc, mk<double>(ps.o.x, ps.o.y, ps.o.z), mk<double>(ps.dhat.x, ps.dhat.y, ps.dhat.z), (double)ps.tmin_n, ps.self_code,
+                        mk<double>(ps.self_n.x, ps.self_n.y, ps.self_n.z), &td, &idx);
+        t_hit = (T)td; code = idx;
+    }
+    if (!active) return false;
+    ++*n_rays;
+    if (idx < 0) {                                                            // miss: sky (main.rs:54-56)
+        *radiance = ps.thr * sky(ps.dhat);
+        return false;
+    }
+    V3<T> cen; T rad; V3<T> albedo; T param;
+    if (sizeof(T) == 4) {
+        const float4 s = sc.sph[idx], m = sc.mat[idx];
+        cen = mk<T>(s.x, s.y, s.z); rad = s.w; albedo = mk<T>(m.x, m.y, m.z); param = m.w;
+    } else {
+        const double4 s = sc.sphd[idx], m = sc.matd[idx];
+        cen = mk<T>(s.x, s.y, s.z); rad = s.w; albedo = mk<T>(m.x, m.y, m.z); param = m.w;
+    }
+    const int kind = sc.kind[idx];
+    const V3<T> p = ps.o + ps.dhat * t_hit;                                   // ray.rs:15-17
+    V3<T> n; bool ff; hit_record(p, cen, rad, ps.dhat, &n, &ff);             // sphere.rs:36-39
+    ++ps.bounce;
+    const Uniform4<T> u = event_uniforms<T>(seed, ps.pix_key, ps.smp, ps.bounce);
+    V3<T> sample;
+    if (kind == MAT_LAMBERTIAN) sample = direct_unit_vector(u.u0, u.u1);      // materials.rs:23
+    else if (kind == MAT_METAL) sample = direct_in_unit_sphere(u.u0, u.u1, u.u2);   // materials.rs:53
+    else sample = mk<T>(u.u0, 0, 0);                                          // materials.rs:96
+    V3<T> att, nd;
+    const bool some = scatter(kind, albedo, param, ps.dhat, n, ff, sample, &att, &nd);   // main.rs:47
+    --ps.depth;
+    if (!some || ps.depth <= 0) {                                             // main.rs:51 / main.rs:40-42: black
+        *radiance = mk<T>(0, 0, 0);
+        return false;
+    }
+    ps.thr = ps.thr * att;                                                    // main.rs:49 as a running product
+    start_ray(ps, p, nd, t_min);
+    ps.self_code = code;
+    ps.self_n = unit_vector(p - cen);
+    return true;
+}
+
 template <typename T, bool kSmem, int kThreads, int kMinCtas>
 __global__ void __launch_bounds__(kThreads, kMinCtas) render_kernel(const RenderArgs<T> a)
 {
@@ -72,10 +146,9 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) render_kernel(const Render
 
     // ---- per-lane path state ----------------------------------------------------------------
     bool active = false;
-    V3<T> o = mk<T>(0, 0, 0), dhat = mk<T>(0, 1, 0), thr = mk<T>(0, 0, 0);
-    T tmin_n = T(0);
-    uint32_t pix_key = 0, smp = 0, bounce = 0;
-    int depth = 0;
+    PathState<T> ps;
+    ps.o = mk<T>(0, 0, 0); ps.dhat = mk<T>(0, 1, 0); ps.thr = mk<T>(0, 0, 0); ps.self_n = mk<T>(0, 1, 0);
+    ps.tmin_n = T(0); ps.self_code = RT_SELF_NONE; ps.pix_key = 0; ps.smp = 0; ps.bounce = 0; ps.depth = 0;
     uint32_t acc_lp = 0xffffffffu;                      // local pixel the accumulators belong to
     unsigned long long acc_r = 0, acc_g = 0, acc_b = 0;
     uint32_t n_rays = 0;
@@ -116,73 +189,28 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) render_kernel(const Render
                     }
                     acc_lp = c_lp; acc_r = acc_g = acc_b = 0;
                 }
-                smp = cs + r;
+                ps.smp = cs + r;
                 const uint32_t j = a.height - 1u - c_y;                 // j = 0 is the bottom row (main.rs:132,141-145)
-                pix_key = j * a.width + c_x;
-                const Uniform4<T> u = event_uniforms<T>(a.seed, pix_key, smp, 0u);
+                ps.pix_key = j * a.width + c_x;
+                const Uniform4<T> u = event_uniforms<T>(a.seed, ps.pix_key, ps.smp, 0u);
                 const T su = (T(c_x) + u.u0) / T(a.width - 1u);         // main.rs:131
                 const T sv = (T(j) + u.u1) / T(a.height - 1u);          // main.rs:132
                 T dx, dy; direct_disk(u.u2, u.u3, &dx, &dy);            // camera.rs:48
-                V3<T> d; get_ray(a.cam, su, sv, dx, dy, &o, &d);        // main.rs:134
-                const T len = length(d);
-                dhat = d * (T(1) / len);
-                tmin_n = a.t_min * len;                                 // t is measured in |dir| units (Appendix C.3)
-                thr = mk<T>(1, 1, 1);
-                depth = a.max_depth; bounce = 0;
-                active = depth > 0;                                      // main.rs:40-42
+                V3<T> ro, rd; get_ray(a.cam, su, sv, dx, dy, &ro, &rd); // main.rs:134
+                start_ray(ps, ro, rd, a.t_min);
+                ps.thr = mk<T>(1, 1, 1); ps.self_code = RT_SELF_NONE;
+                ps.depth = a.max_depth; ps.bounce = 0;
+                active = ps.depth > 0;                                   // main.rs:40-42
             }
             cs += min((uint32_t)__popc(need), avail);
             need = __ballot_sync(RT_FULL, !active);
         }
         if (!__any_sync(RT_FULL, active)) break;
 
-        // ---- world.hit(r, t_min, INFINITY) (main.rs:44): all 32 lanes scan together ----------------
-        T t_hit; int idx;
-        if (sizeof(T) == 4) {
-            HitF h = closest_hit<kSmem>(a.scene, soa, mk<float>((float)o.x, (float)o.y, (float)o.z),
-                                        mk<float>((float)dhat.x, (float)dhat.y, (float)dhat.z), (float)tmin_n, cand, kThreads);
-            t_hit = (T)h.t; idx = h.idx;
-        } else {
-            double td; closest_hit_f64(a.scene, mk<double>(o.x, o.y, o.z), mk<double>(dhat.x, dhat.y, dhat.z), (double)tmin_n, &td, &idx);
-            t_hit = (T)td;
-        }
-
-        if (active) {
-            ++n_rays;
-            if (idx < 0) {                                               // miss: sky (main.rs:54-56)
-                const V3<T> c = thr * sky(dhat);
-                acc_r += to_fix(c.x); acc_g += to_fix(c.y); acc_b += to_fix(c.z);
-                active = false;
-            } else {
-                V3<T> cen; T rad; V3<T> albedo; T param;
-                if (sizeof(T) == 4) {
-                    const float4 s = a.scene.sph[idx], m = a.scene.mat[idx];
-                    cen = mk<T>(s.x, s.y, s.z); rad = s.w; albedo = mk<T>(m.x, m.y, m.z); param = m.w;
-                } else {
-                    const double4 s = a.scene.sphd[idx], m = a.scene.matd[idx];
-                    cen = mk<T>(s.x, s.y, s.z); rad = s.w; albedo = mk<T>(m.x, m.y, m.z); param = m.w;
-                }
-                const int kind = a.scene.kind[idx];
-                const V3<T> p = o + dhat * t_hit;                        // ray.rs:15-17
-                V3<T> n; bool ff; hit_record(p, cen, rad, dhat, &n, &ff);  // sphere.rs:36-39
-                ++bounce;
-                const Uniform4<T> u = event_uniforms<T>(a.seed, pix_key, smp, bounce);
-                V3<T> sample;
-                if (kind == MAT_LAMBERTIAN) sample = direct_unit_vector(u.u0, u.u1);
-                else if (kind == MAT_METAL) sample = direct_in_unit_sphere(u.u0, u.u1, u.u2);
-                else sample = mk<T>(u.u0, 0, 0);
-                V3<T> att, nd;
-                const bool some = scatter(kind, albedo, param, dhat, n, ff, sample, &att, &nd);   // main.rs:47
-                --depth;
-                if (!some || depth <= 0) {                                // main.rs:51 / main.rs:40-42: black
-                    active = false;
-                } else {
-                    thr = thr * att;                                      // main.rs:49 as a running product
-                    const T len = length(nd);
-                    o = p; dhat = nd * (T(1) / len); tmin_n = a.t_min * len;
-                }
-            }
-        }
+        V3<T> rad = mk<T>(0, 0, 0);
+        const bool was = active;
+        active = bounce_step<T, kSmem>(a.scene, soa, cand, kThreads, a.seed, a.t_min, active, ps, &rad, &n_rays);
+        if (was && !active) { acc_r += to_fix(rad.x); acc_g += to_fix(rad.y); acc_b += to_fix(rad.z); }   // pixel_color += ray_color (main.rs:135)
     }
     if (acc_lp != 0xffffffffu) {
         atomicAdd(a.accum + acc_lp, acc_r);

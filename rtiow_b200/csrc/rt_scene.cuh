@@ -43,7 +43,9 @@ struct SceneDev {
 struct HitF {           // closest hit so far; t in units of the normalised direction
     float t;
     int idx;            // index in the reference's list, -1 = none
+    int code;           // where the winner lives: >= 0 position in `small`, <= -2 : -2 - position in `big`, -1 none
 };
+#define RT_SELF_NONE (-1)
 
 // Precise test of one candidate (sphere.rs:16-34 via sphere_roots), index-aware acceptance.
 // The reference scans in list order and accepts root <= closest_so_far, so among equal roots the
@@ -59,6 +61,20 @@ __device__ __forceinline__ void candidate(V3<T> o, V3<T> dhat, T inv_a, T t_min,
     if (t < *t_best || (t == *t_best && idx > *i_best)) { *t_best = t; *i_best = idx; }
 }
 
+// The sphere a ray STARTS on (the one it just scattered from).  In f64 the reference's origin is within
+// ~1e-15 of that surface, so its near-zero root never reaches t_min = 1e-4 (main.rs:44); an f32 origin
+// is ~1e-6 off, which t_min * |dir| does not cover when the scattered direction is short
+// (Lambertian normal + unit vector, materials.rs:23).  For that one sphere the origin is therefore
+// taken ON the surface (centre + self_n * |r|, self_n = unit(p - centre)): the roots are exactly
+// {0, 2 tca}, the zero root is dropped as sphere.rs:29 drops it, and only 2 tca is offered.
+template <typename T>
+__device__ __forceinline__ void candidate_self(V3<T> dhat, T inv_a, T t_min, V3<T> self_n, T r, int idx, T* t_best, int* i_best)
+{
+    const T t = T(-2) * abs_t(r) * dot(self_n, dhat) * inv_a;      // oc = -|r| self_n ; t = 2 (oc . dhat) / a
+    if (!(t >= t_min)) return;
+    if (t < *t_best || (t == *t_best && idx > *i_best)) { *t_best = t; *i_best = idx; }
+}
+
 // The f32 scan over the shared-memory SoA.
 //   filter (all spheres, branch-free, packed f32x2 over sphere pairs):
 //       oc = c - o;  hb = oc . d';  disc' = hb^2 - |oc|^2 + r2f        (10 packed ops per 2 tests)
@@ -69,7 +85,7 @@ __device__ __forceinline__ void candidate(V3<T> o, V3<T> dhat, T inv_a, T t_min,
 // s_soa: [4][np] floats in shared memory (or global when the scene does not fit).
 template <bool kSmem>
 __device__ __forceinline__ void scan_small(const float* __restrict__ s_soa, int np, const float4* __restrict__ small,
-                                           V3<float> o, V3<float> dhat, float inv_a, float t_min,
+                                           V3<float> o, V3<float> dhat, float inv_a, float t_min, int self_pos, V3<float> self_n,
                                            uint16_t* cand, int cand_stride, float* t_best, int* p_best)
 {
     const int n4 = np >> 2;
@@ -111,7 +127,11 @@ __device__ __forceinline__ void scan_small(const float* __restrict__ s_soa, int 
                 c &= ~(0x80000000u >> k);
                 const int p = (w << 5) + k;
                 if (nc < RT_CAND_CAP) { cand[nc * cand_stride] = (uint16_t)(p - (w0 << 5)); ++nc; }
-                else { const float4 s = small[p]; candidate<float>(o, dhat, inv_a, t_min, mk(s.x, s.y, s.z), s.w, p, &tb, &pb); }
+                else {
+                    const float4 s = small[p];
+                    if (p == self_pos) candidate_self<float>(dhat, inv_a, t_min, self_n, s.w, p, &tb, &pb);
+                    else candidate<float>(o, dhat, inv_a, t_min, mk(s.x, s.y, s.z), s.w, p, &tb, &pb);
+                }
             }
         }
         const int nmax = __reduce_max_sync(RT_FULL, nc);
@@ -119,7 +139,8 @@ __device__ __forceinline__ void scan_small(const float* __restrict__ s_soa, int 
             if (k < nc) {
                 const int p = (w0 << 5) + cand[k * cand_stride];
                 const float4 s = small[p];
-                candidate<float>(o, dhat, inv_a, t_min, mk(s.x, s.y, s.z), s.w, p, &tb, &pb);
+                if (p == self_pos) candidate_self<float>(dhat, inv_a, t_min, self_n, s.w, p, &tb, &pb);
+                else candidate<float>(o, dhat, inv_a, t_min, mk(s.x, s.y, s.z), s.w, p, &tb, &pb);
             }
         }
     }
@@ -128,38 +149,49 @@ __device__ __forceinline__ void scan_small(const float* __restrict__ s_soa, int 
 
 // Closest hit of one ray against the whole scene: HittableList::hit (mod.rs:56-69).
 // float: packed filter over the small spheres + f64 test of the big ones; all lanes of the warp
-// must call together.  Returns t in dhat units and the list index (or -1).
+// must call together.  self_code / self_n identify the sphere the ray starts on (RT_SELF_NONE for
+// camera rays).  Returns t in dhat units, the list index (or -1) and the winner's code.
 template <bool kSmem>
 __device__ __forceinline__ HitF closest_hit(const SceneDev& sc, const float* s_soa, V3<float> o, V3<float> dhat, float t_min,
-                                            uint16_t* cand, int cand_stride)
+                                            int self_code, V3<float> self_n, uint16_t* cand, int cand_stride)
 {
     const float inv_a = 1.0f / length_squared(dhat);
     float tb = __int_as_float(0x7f800000);   // f64::INFINITY at main.rs:44
     int pb = -1;
-    scan_small<kSmem>(s_soa, sc.np, sc.small, o, dhat, inv_a, t_min, cand, cand_stride, &tb, &pb);
-    HitF h; h.t = tb; h.idx = pb >= 0 ? sc.small_idx[pb] : -1;
+    scan_small<kSmem>(s_soa, sc.np, sc.small, o, dhat, inv_a, t_min, self_code, self_n, cand, cand_stride, &tb, &pb);
+    HitF h; h.t = tb; h.idx = pb >= 0 ? sc.small_idx[pb] : -1; h.code = pb;
     if (sc.nb > 0) {
         const V3<double> od = mk<double>(o.x, o.y, o.z), dd = mk<double>(dhat.x, dhat.y, dhat.z);
         const double inv_ad = 1.0 / length_squared(dd);
         double tbd = (double)h.t; int ib = h.idx;
         for (int b = 0; b < sc.nb; ++b) {
             const double4 s = sc.big[b];
-            candidate<double>(od, dd, inv_ad, (double)t_min, mk(s.x, s.y, s.z), s.w, sc.big_idx[b], &tbd, &ib);
+            const int before = ib; const double tbefore = tbd;
+            if (self_code == -2 - b) {
+                V3<double> sn = mk<double>(self_n.x, self_n.y, self_n.z);
+                sn = sn * (1.0 / sqrt(length_squared(sn)));
+                candidate_self<double>(dd, inv_ad, (double)t_min, sn, s.w, sc.big_idx[b], &tbd, &ib);
+            } else {
+                candidate<double>(od, dd, inv_ad, (double)t_min, mk(s.x, s.y, s.z), s.w, sc.big_idx[b], &tbd, &ib);
+            }
+            if (ib != before || tbd != tbefore) { h.idx = ib; h.t = (float)tbd; h.code = -2 - b; }
         }
-        if (ib != h.idx) { h.idx = ib; h.t = (float)tbd; }
     }
     return h;
 }
 
 // double: the reference's arithmetic width, every sphere through the precise test (triage mode).
-__device__ __forceinline__ void closest_hit_f64(const SceneDev& sc, V3<double> o, V3<double> dhat, double t_min, double* t_out, int* idx_out)
+// code == list index here.
+__device__ __forceinline__ void closest_hit_f64(const SceneDev& sc, V3<double> o, V3<double> dhat, double t_min, int self_idx, V3<double> self_n,
+                                                double* t_out, int* idx_out)
 {
     const double inv_a = 1.0 / length_squared(dhat);
     double tb = __longlong_as_double(0x7ff0000000000000LL);
     int ib = -1;
     for (int i = 0; i < sc.n; ++i) {
         const double4 s = sc.sphd[i];
-        candidate<double>(o, dhat, inv_a, t_min, mk(s.x, s.y, s.z), s.w, i, &tb, &ib);
+        if (i == self_idx) candidate_self<double>(dhat, inv_a, t_min, self_n, s.w, i, &tb, &ib);
+        else candidate<double>(o, dhat, inv_a, t_min, mk(s.x, s.y, s.z), s.w, i, &tb, &ib);
     }
     *t_out = tb; *idx_out = ib;
 }

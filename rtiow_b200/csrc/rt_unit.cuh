@@ -53,10 +53,10 @@ __global__ void __launch_bounds__(kThreads) hitlist_kernel(SceneDev sc, int64_t 
     T th; int idx;
     if (sizeof(T) == 4) {
         HitF h = closest_hit<kSmem>(sc, soa, mk<float>((float)o.x, (float)o.y, (float)o.z), mk<float>((float)dhat.x, (float)dhat.y, (float)dhat.z),
-                                    (float)tmin_n, cand, kThreads);
+                                    (float)tmin_n, RT_SELF_NONE, mk<float>(0, 1, 0), cand, kThreads);
         th = (T)h.t; idx = h.idx;
     } else {
-        double td; closest_hit_f64(sc, mk<double>(o.x, o.y, o.z), mk<double>(dhat.x, dhat.y, dhat.z), (double)tmin_n, &td, &idx);
+        double td; closest_hit_f64(sc, mk<double>(o.x, o.y, o.z), mk<double>(dhat.x, dhat.y, dhat.z), (double)tmin_n, RT_SELF_NONE, mk<double>(0, 1, 0), &td, &idx);
         th = (T)td;
     }
     if (!live) return;
@@ -149,45 +149,17 @@ __global__ void __launch_bounds__(kThreads) ray_color_kernel(SceneDev sc, int64_
     uint16_t* cand = cand_base + threadIdx.x;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool active = i < n && max_depth > 0;
-    V3<T> o = mk<T>(0, 0, 0), dhat = mk<T>(0, 1, 0), thr = mk<T>(1, 1, 1), result = mk<T>(0, 0, 0);
-    T tmin_n = T(0); uint32_t pk = 0, sm = 0, bounce = 0; int depth = max_depth; unsigned long long nr = 0;
-    if (i < n) {
-        o = ld3<T>(orig, i); const V3<T> d = ld3<T>(dir, i); const T len = length(d);
-        dhat = d * (T(1) / len); tmin_n = (T)t_min * len; pk = pixel[i]; sm = sample[i];
-    }
+    PathState<T> ps;
+    ps.o = mk<T>(0, 0, 0); ps.dhat = mk<T>(0, 1, 0); ps.thr = mk<T>(1, 1, 1); ps.self_n = mk<T>(0, 1, 0);
+    ps.tmin_n = T(0); ps.self_code = RT_SELF_NONE; ps.pix_key = 0; ps.smp = 0; ps.bounce = 0; ps.depth = max_depth;
+    V3<T> result = mk<T>(0, 0, 0);
+    uint32_t nr = 0;
+    if (i < n) { start_ray(ps, ld3<T>(orig, i), ld3<T>(dir, i), (T)t_min); ps.pix_key = pixel[i]; ps.smp = sample[i]; }
     while (__any_sync(RT_FULL, active)) {
-        T t_hit; int idx;
-        if (sizeof(T) == 4) {
-            HitF h = closest_hit<kSmem>(sc, soa, mk<float>((float)o.x, (float)o.y, (float)o.z), mk<float>((float)dhat.x, (float)dhat.y, (float)dhat.z),
-                                        (float)tmin_n, cand, kThreads);
-            t_hit = (T)h.t; idx = h.idx;
-        } else {
-            double td; closest_hit_f64(sc, mk<double>(o.x, o.y, o.z), mk<double>(dhat.x, dhat.y, dhat.z), (double)tmin_n, &td, &idx);
-            t_hit = (T)td;
-        }
-        if (active) {
-            ++nr;
-            if (idx < 0) { result = thr * sky(dhat); active = false; }
-            else {
-                V3<T> cen; T rad; V3<T> albedo; T param;
-                if (sizeof(T) == 4) { const float4 s = sc.sph[idx], m = sc.mat[idx]; cen = mk<T>(s.x, s.y, s.z); rad = s.w; albedo = mk<T>(m.x, m.y, m.z); param = m.w; }
-                else { const double4 s = sc.sphd[idx], m = sc.matd[idx]; cen = mk<T>(s.x, s.y, s.z); rad = s.w; albedo = mk<T>(m.x, m.y, m.z); param = m.w; }
-                const int kind = sc.kind[idx];
-                const V3<T> p = o + dhat * t_hit;
-                V3<T> nn; bool ff; hit_record(p, cen, rad, dhat, &nn, &ff);
-                ++bounce;
-                const Uniform4<T> u = event_uniforms<T>(seed, pk, sm, bounce);
-                V3<T> smp;
-                if (kind == MAT_LAMBERTIAN) smp = direct_unit_vector(u.u0, u.u1);
-                else if (kind == MAT_METAL) smp = direct_in_unit_sphere(u.u0, u.u1, u.u2);
-                else smp = mk<T>(u.u0, 0, 0);
-                V3<T> att, nd;
-                const bool some = scatter(kind, albedo, param, dhat, nn, ff, smp, &att, &nd);
-                --depth;
-                if (!some || depth <= 0) active = false;
-                else { thr = thr * att; const T len = length(nd); o = p; dhat = nd * (T(1) / len); tmin_n = (T)t_min * len; }
-            }
-        }
+        V3<T> rad = mk<T>(0, 0, 0);
+        const bool was = active;
+        active = bounce_step<T, kSmem>(sc, soa, cand, kThreads, seed, (T)t_min, active, ps, &rad, &nr);
+        if (was && !active) result = rad;
     }
     if (i < n) { st3(color, i, result); if (rays) rays[i] = nr; }
 }

@@ -54,8 +54,9 @@ def ctx(capi):
     c.close()
 
 
-@pytest.fixture(scope="session")
+@pytest.fixture()
 def ctx_final(ctx, final_scene):
+    """ctx with the final scene uploaded (re-uploaded per test: other tests replace the scene)."""
     ctx.upload_scene(**final_scene[0])
     return ctx
 

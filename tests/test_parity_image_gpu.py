@@ -1,0 +1,177 @@
+"""GPU suite, image level: rtiow_render (the drop-in for main.rs:122-145) against the oracle's render of the same
+explicit scene.
+
+Three strengths of comparison:
+  * SAME PATHS.  The oracle's DIRECT sampler consumes the same Philox blocks as the GPU, so the f64 GPU render must
+    reproduce the oracle's image essentially bit for bit, and the f32 render must differ only where f32 rounding
+    flipped a knife-edge decision (rare, bounded).
+  * STATISTICAL (the bound stated in BASELINE.md): against the oracle's reference-faithful REJECTION sampler,
+    RMSE(gpu, oracle) <= 1.25 x RMSE(oracle seed A, oracle seed B) at equal spp, per-channel mean within 0.1/255
+    (+ the Monte-Carlo standard error of that mean at test sizes), sky-only pixels within 1 LSB.
+  * SIZE-INDEPENDENT PROPERTIES at BASELINE's full frame sizes: determinism, invariance to the row-tile partition
+    (any world size / tile height gives the same bytes), ray counts, alpha, empty scenes.
+"""
+import numpy as np
+import pytest
+
+from conftest import final_camera
+
+pytestmark = pytest.mark.gpu
+
+
+def rmse(a, b):
+    return float(np.sqrt(((a[..., :3].astype(float) - b[..., :3].astype(float)) ** 2).mean()))
+
+
+def render_gpu(ctx, capi, cam, **kw):
+    return ctx.render(cam, capi.default_params(**kw))
+
+
+def test_cfg1_same_paths_f64(ctx_final, capi, oracle, final_scene):
+    """BASELINE configs[0]: 400x225, 10 spp, depth 50 — the reference's own CPU-runnable case."""
+    _, sc = final_scene
+    W, H, spp = 400, 225, 10
+    ref, _, cnt = oracle.render(sc, final_camera(oracle, W / H), W, H, spp, seed=1, sampler=oracle.SAMPLER_DIRECT)
+    img, st = render_gpu(ctx_final, capi, final_camera(capi, W / H), width=W, height=H, spp=spp, seed=1, precision=capi.F64)
+    diff = np.abs(img.astype(int) - ref.astype(int))
+    assert (diff > 0).mean() < 2e-4, f"f64 GPU render differs from the oracle on {(diff > 0).sum()} bytes"
+    assert diff.max() <= 2 or (diff > 2).sum() <= 6
+    assert st["rays_traced"] == cnt["rays"] or abs(st["rays_traced"] - cnt["rays"]) < 1e-5 * cnt["rays"]
+    assert st["paths"] == W * H * spp and st["sphere_tests"] == st["rays_traced"] * sc.n
+
+
+def test_cfg1_same_paths_f32(ctx_final, capi, oracle, final_scene):
+    _, sc = final_scene
+    W, H, spp = 400, 225, 10
+    ref, _, cnt = oracle.render(sc, final_camera(oracle, W / H), W, H, spp, seed=1, sampler=oracle.SAMPLER_DIRECT)
+    img, st = render_gpu(ctx_final, capi, final_camera(capi, W / H), width=W, height=H, spp=spp, seed=1)
+    diff = np.abs(img[..., :3].astype(int) - ref[..., :3].astype(int)).max(axis=2)
+    assert (diff <= 1).mean() > 0.995, f"{(diff > 1).mean():.4%} of pixels differ by more than 1 LSB"
+    assert rmse(img, ref) < 1.5                      # two independent seeds at 10 spp differ by RMSE ~ 12.8
+    assert abs(st["rays_traced"] / cnt["rays"] - 1) < 2e-3
+    assert (img[..., 3] == 255).all()
+
+
+def test_statistical_parity_vs_reference_sampler(ctx_final, capi, oracle, final_scene):
+    """the stated bound, against the reference-faithful rejection sampler with independent streams"""
+    _, sc = final_scene
+    W, H, spp = 256, 144, 64
+    ocam = final_camera(oracle, W / H)
+    a, acc_a, _ = oracle.render(sc, ocam, W, H, spp, seed=101, sampler=oracle.SAMPLER_REJECTION, want_accum=True)
+    b, acc_b, _ = oracle.render(sc, ocam, W, H, spp, seed=202, sampler=oracle.SAMPLER_REJECTION, want_accum=True)
+    img, _ = render_gpu(ctx_final, capi, final_camera(capi, W / H), width=W, height=H, spp=spp, seed=303)
+    floor = rmse(a, b)
+    assert rmse(img, a) <= 1.25 * floor and rmse(img, b) <= 1.25 * floor, (rmse(img, a), rmse(img, b), floor)
+    # bias: per-channel mean of 8-bit values; tolerance 0.1 + 3 standard errors of the mean difference at this size
+    se = np.sqrt(2) * floor / np.sqrt(W * H)
+    for c in range(3):
+        assert abs(img[..., c].astype(float).mean() - a[..., c].astype(float).mean()) <= 0.1 + 3 * se
+    # sky-only pixels (top rows of this camera) within 1 LSB
+    assert np.abs(img[:8, :, :3].astype(int) - a[:8, :, :3].astype(int)).max() <= 1
+
+
+@pytest.mark.parametrize("mode,name", [(1, "all-Lambertian"), (2, "all-Metal"), (3, "all-Dialectric + hollow shell")])
+def test_material_isolation_scenes(ctx, capi, oracle, scene_factory, mode, name):
+    """BASELINE configs[2] (reduced size): divergence-stress scenes, same-path comparison per material"""
+    arrays, sc = scene_factory(seed=2, mode=mode)
+    ctx.upload_scene(**arrays)
+    W, H, spp = 320, 180, 8
+    ref, _, cnt = oracle.render(sc, final_camera(oracle, W / H), W, H, spp, seed=5, sampler=oracle.SAMPLER_DIRECT)
+    img, st = render_gpu(ctx, capi, final_camera(capi, W / H), width=W, height=H, spp=spp, seed=5)
+    diff = np.abs(img[..., :3].astype(int) - ref[..., :3].astype(int)).max(axis=2)
+    assert (diff <= 1).mean() > 0.99, f"{name}: {(diff > 1).mean():.4%} pixels off by > 1 LSB"
+    assert abs(st["rays_traced"] / cnt["rays"] - 1) < 5e-3
+    img64, _ = render_gpu(ctx, capi, final_camera(capi, W / H), width=W, height=H, spp=spp, seed=5, precision=capi.F64)
+    assert (np.abs(img64.astype(int) - ref.astype(int)) > 0).mean() < 5e-4
+
+
+def test_many_spheres_scene(ctx, capi, oracle, scene_factory):
+    """BASELINE configs[3] shape (10k spheres: filter SoA exceeds the small-scene shared-memory layout), tiny frame"""
+    arrays, sc = scene_factory(seed=3, half_extent=50)
+    assert sc.n > 10_000
+    ctx.upload_scene(**arrays)
+    W, H, spp = 96, 54, 2
+    ref, _, cnt = oracle.render(sc, final_camera(oracle, W / H), W, H, spp, seed=8, sampler=oracle.SAMPLER_DIRECT)
+    img, st = render_gpu(ctx, capi, final_camera(capi, W / H), width=W, height=H, spp=spp, seed=8)
+    diff = np.abs(img[..., :3].astype(int) - ref[..., :3].astype(int)).max(axis=2)
+    assert (diff <= 1).mean() > 0.99
+    assert abs(st["rays_traced"] / cnt["rays"] - 1) < 1e-2
+
+
+def test_determinism_and_seed(ctx_final, capi):
+    cam = final_camera(capi, 16 / 9)
+    a, sa = render_gpu(ctx_final, capi, cam, width=320, height=180, spp=16, seed=1)
+    b, sb = render_gpu(ctx_final, capi, cam, width=320, height=180, spp=16, seed=1)
+    c, _ = render_gpu(ctx_final, capi, cam, width=320, height=180, spp=16, seed=2)
+    assert np.array_equal(a, b) and sa["rays_traced"] == sb["rays_traced"]       # bit-identical run to run
+    assert not np.array_equal(a, c) and rmse(a, c) < 15
+
+
+@pytest.mark.parametrize("W,H,spp", [(1200, 675, 2), (400, 225, 10), (201, 133, 3)])
+def test_tile_partition_invariance(ctx_final, capi, W, H, spp):
+    """N-GPU image == 1-GPU image, bit for bit: ranks are emulated one after another on this GPU through the
+    per-rank entry points the torchrun path uses (rtiow_render_tiles_device + rtiow_deinterleave_device)."""
+    import torch
+    cam = final_camera(capi, W / H)
+    base, _ = ctx_final.render(cam, capi.default_params(width=W, height=H, spp=spp, seed=4))
+    for world, tile_rows in [(2, 4), (8, 4), (8, 1), (3, 7), (4, 64)]:
+        prm = capi.default_params(width=W, height=H, spp=spp, seed=4, tile_rows=tile_rows)
+        nbytes = ctx_final.tile_buffer_bytes(prm, world)
+        gathered = torch.zeros(world * nbytes, dtype=torch.uint8, device="cuda")
+        rays = 0
+        for rank in range(world):
+            tiles = gathered[rank * nbytes:(rank + 1) * nbytes]
+            st = ctx_final.render_tiles_device(cam, prm, rank, world, tiles.data_ptr(), 0, want_stats=True)
+            rays += st["rays_traced"]
+        frame = torch.empty(H * W * 4, dtype=torch.uint8, device="cuda")
+        ctx_final.deinterleave_device(gathered.data_ptr(), prm, world, frame.data_ptr(), 0)
+        torch.cuda.synchronize()
+        got = frame.cpu().numpy().reshape(H, W, 4)
+        assert np.array_equal(got, base), f"world={world} tile_rows={tile_rows}: image differs from the single-GPU image"
+
+
+def test_full_size_properties_cfg2(ctx_final, capi, oracle, final_scene):
+    """BASELINE configs[1] frame (1200x675) at reduced spp: top-down orientation, alpha, ray statistics, sky rows."""
+    _, sc = final_scene
+    W, H, spp = 1200, 675, 4
+    img, st = render_gpu(ctx_final, capi, final_camera(capi, W / H), width=W, height=H, spp=spp, seed=1)
+    assert img.shape == (H, W, 4) and (img[..., 3] == 255).all()
+    assert st["paths"] == W * H * spp and 2.4 < st["rays_traced"] / st["paths"] < 2.9          # SURVEY: ~2.66 rays/path
+    # top rows are sky: blue-ish, smooth; bottom rows are ground/spheres
+    top = img[:20, :, :3].astype(float)
+    assert top[..., 2].min() >= 254 and top.std(axis=1).max() < 1.5
+    ref, _, _ = oracle.render(sc, final_camera(oracle, W / H), W, H, spp, seed=1, sampler=oracle.SAMPLER_DIRECT, rows=(0, 12))
+    assert np.abs(img[:12, :, :3].astype(int) - ref[:12, :, :3].astype(int)).max() <= 1
+    # a band through the middle of the frame against the oracle (same paths)
+    ref_mid, _, _ = oracle.render(sc, final_camera(oracle, W / H), W, H, spp, seed=1, sampler=oracle.SAMPLER_DIRECT, rows=(400, 408))
+    d = np.abs(img[400:408, :, :3].astype(int) - ref_mid[400:408, :, :3].astype(int)).max(axis=2)
+    assert (d <= 1).mean() > 0.99
+
+
+def test_empty_world_and_edge_params(ctx, capi, oracle):
+    ctx.upload_scene(np.zeros((0, 3)), np.zeros(0), np.zeros(0, np.uint32), [0], [[1, 1, 1]], [0])
+    cam = final_camera(capi, 1.5)
+    img, st = render_gpu(ctx, capi, cam, width=64, height=43, spp=3, seed=1, alpha=7)
+    assert st["rays_traced"] == 64 * 43 * 3 and (img[..., 3] == 7).all() and img[..., 2].min() == 255
+    # max_depth 0: every path is black (main.rs:40-42), no ray is traced
+    img0, st0 = render_gpu(ctx, capi, cam, width=64, height=43, spp=3, max_depth=0)
+    assert st0["rays_traced"] == 0 and (img0[..., :3] == 0).all()
+    # smallest legal frame, spp 1
+    img1, _ = render_gpu(ctx, capi, cam, width=2, height=2, spp=1)
+    assert img1.shape == (2, 2, 4)
+    for bad in (dict(width=1), dict(height=1), dict(spp=0), dict(tile_rows=0), dict(precision=9)):
+        with pytest.raises(capi.RtiowError) as e:
+            render_gpu(ctx, capi, cam, **{**dict(width=8, height=8, spp=1), **bad})
+        assert e.value.code == capi.ERR_INVALID_ARG
+
+
+def test_unsupported_and_invalid_scene(ctx, capi):
+    with pytest.raises(capi.RtiowError) as e:
+        ctx.upload_scene([[0, 0, 0]], [1.0], [0], [3], [[1, 1, 1]], [0])          # unknown material kind: no CPU fallback
+    assert e.value.code == capi.ERR_UNSUPPORTED
+    with pytest.raises(capi.RtiowError) as e:
+        ctx.upload_scene([[0, 0, 0]], [1.0], [5], [0], [[1, 1, 1]], [0])          # material index out of range
+    assert e.value.code == capi.ERR_INVALID_ARG
+    with pytest.raises(capi.RtiowError) as e:
+        ctx.upload_scene([[np.nan, 0, 0]], [1.0], [0], [0], [[1, 1, 1]], [0])
+    assert e.value.code == capi.ERR_INVALID_ARG
