@@ -103,7 +103,8 @@ def oracle_world(scene_arrays):
 def time_oracle(o, sc, W, H, spp, seed):
     cam = o.camera_new((13, 2, 3), (0, 0, 0), (0, 1, 0), 20.0, W / H, 0.1, 10.0)
     t0 = time.perf_counter()
-    _, _, cnt = o.render(sc, cam, W, H, spp, seed=seed, sampler=o.SAMPLER_REJECTION)
+    # n_threads explicit: torchrun exports OMP_NUM_THREADS=1, the reference arm must use every host core
+    _, _, cnt = o.render(sc, cam, W, H, spp, seed=seed, sampler=o.SAMPLER_REJECTION, n_threads=o.host_threads())
     dt = time.perf_counter() - t0
     return W * H * spp / dt / 1e6, dt, cnt
 
@@ -282,7 +283,7 @@ def run_ours(args, rank, local_rank, world):
                     "h2d_bytes_per_step": scene_bytes + 176 + 48, "d2h_bytes_per_step": W * H * 4 + 16},
             "gpu_launches": n_launch,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": None,
-                         "kernel": "rt::render_kernel<float,true,256,4>", "kernel_ms": kms, "flop_per_test": FLOP_PER_TEST,
+                         "kernel": "rt::render_kernel<float,true,256,3>", "kernel_ms": kms, "flop_per_test": FLOP_PER_TEST,
                          "rays_per_path": rays_total / paths, "sphere_tests_per_launch": rays_total * n_spheres / world,
                          "peak_source": "FFMA2 calibration kernel in this run (rtiow_fp32_peak_probe, ~300 ms); MEASURED_PEAKS.json has no FP32 entry",
                          "peak_scalar_ffma": peak_scalar_tflops, "peak_nominal": FP32_NOMINAL_TFLOPS},

@@ -11,6 +11,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -192,11 +193,15 @@ extern "C" int rtiow_scene_upload(rtiow_ctx* c, const rtiow_spheres* s, const rt
         if (p < ns) {
             const float4 v = sph[small_ids[p]];
             soa[p] = v.x; soa[np + p] = v.y; soa[2 * (size_t)np + p] = v.z;
-            // filter radius^2 inflated by 2^-20 (+ a denormal-safe floor): see RT_FILTER_DIR_SCALE
-            soa[3 * (size_t)np + p] = v.w * v.w * 1.00000095367431640625f + 1e-30f;
+            // K = |c|^2 - r^2 of the f32 sphere, in f64, lowered by the filter slack (RT_FILTER_SLACK, rt_scene.cuh)
+            // and rounded toward -inf: the filter may only err towards keeping a sphere
+            const double c2 = (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z, r2 = (double)v.w * v.w;
+            const double K = c2 - r2 - (double)RT_FILTER_SLACK * (c2 + r2) - 1e-30;
+            float Kf = (float)K; if ((double)Kf > K) Kf = std::nextafterf(Kf, -INFINITY);
+            soa[3 * (size_t)np + p] = Kf;
             small[p] = v; small_idx[p] = small_ids[p];
-        } else {       // padding: |oc|^2 + 1e30 can never be reached by hb^2
-            soa[p] = 0; soa[np + p] = 0; soa[2 * (size_t)np + p] = 0; soa[3 * (size_t)np + p] = -1e30f;
+        } else {       // padding: C = 1e30 can never be reached by hb^2
+            soa[p] = 0; soa[np + p] = 0; soa[2 * (size_t)np + p] = 0; soa[3 * (size_t)np + p] = 1e30f;
             small[p] = make_float4(0, 0, 0, 0); small_idx[p] = -1;
         }
     }
@@ -360,7 +365,17 @@ static int launch_render(DeviceState& d, const rtiow_camera* cam, const rtiow_pa
         k<<<grid, 256, 0, st>>>(a);
     } else {
         const ScanCfg cfg = pick_cfg(d.scene.np);
-        if (cfg.variant == 0) {
+        const char* tune = getenv("RTIOW_TUNE_MIN_CTAS");        // experiment knob (tools/, not a product switch)
+        const int min_ctas = tune ? atoi(tune) : 3;             // 3 CTAs x 256 threads x 80 registers fills the 64K-register file
+        if (cfg.variant == 0 && min_ctas == 3) {
+            auto k = render_kernel<T, true, 256, 3>;
+            int rc = prep_kernel(k, cfg.smem, 256, d.sms, &grid); if (rc) return rc;
+            k<<<grid, 256, cfg.smem, st>>>(a);
+        } else if (cfg.variant == 0 && min_ctas == 2) {
+            auto k = render_kernel<T, true, 256, 2>;
+            int rc = prep_kernel(k, cfg.smem, 256, d.sms, &grid); if (rc) return rc;
+            k<<<grid, 256, cfg.smem, st>>>(a);
+        } else if (cfg.variant == 0) {
             auto k = render_kernel<T, true, 256, 4>;
             int rc = prep_kernel(k, cfg.smem, 256, d.sms, &grid); if (rc) return rc;
             k<<<grid, 256, cfg.smem, st>>>(a);

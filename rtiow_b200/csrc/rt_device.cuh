@@ -156,14 +156,27 @@ template <typename T> __device__ __forceinline__ void get_ray(const CameraT<T>& 
 // oc = centre - origin (the negative of sphere.rs:18, so tca = -half_b/a).
 // Range test and root order are sphere.rs:28-34 verbatim: root == t_max is ACCEPTED.
 // ------------------------------------------------------------------------------------------------
+// sqrt for the f64 test of large-radius spheres inside the f32 renderer: MUFU.RSQ seed + one Newton
+// step in f64 (relative error ~2e-14, far below what t needs) instead of the ~30-instruction IEEE sqrt.
+__device__ __forceinline__ double sqrt_seeded(double x)
+{
+    x = fmax(x, 1e-30);
+    double y = (double)rsqrtf((float)x);
+    y = y * fma(-0.5 * x, y * y, 1.5);
+    return x * y;
+}
+template <bool kSeeded> __device__ __forceinline__ float sqrt_sel(float x) { return sqrtf(x); }
+template <bool kSeeded> __device__ __forceinline__ double sqrt_sel(double x) { return kSeeded ? sqrt_seeded(x) : sqrt(x); }
+
 // inv_a = 1 / |dhat|^2 (dhat is unit only to rounding; hoisted per ray).
-template <typename T> __device__ __forceinline__ bool sphere_roots(V3<T> oc, V3<T> dhat, T inv_a, T r2, T t_min, T t_max, T* root)
+template <typename T, bool kSeededSqrt = false>
+__device__ __forceinline__ bool sphere_roots(V3<T> oc, V3<T> dhat, T inv_a, T r2, T t_min, T t_max, T* root)
 {
     T tca = dot(oc, dhat) * inv_a;
     V3<T> l = oc - dhat * tca;
     T disc = r2 - length_squared(l);
     if (disc < T(0)) return false;                   // sphere.rs:25
-    T sq = sqrt_t(disc * inv_a);
+    T sq = sqrt_sel<kSeededSqrt>(disc * inv_a);
     T t = tca - sq;                                  // sphere.rs:28
     if (t < t_min || t_max < t) {
         t = tca + sq;                                // sphere.rs:30
@@ -240,6 +253,7 @@ template <typename T> __device__ __forceinline__ V3<T> sky(V3<T> dir)
 // ------------------------------------------------------------------------------------------------
 typedef unsigned long long u64;
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { float2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(*(u64*)&d) : "l"(*(u64*)&a), "l"(*(u64*)&b), "l"(*(u64*)&c)); return d; }
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) { float2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(*(u64*)&d) : "l"(*(u64*)&a), "l"(*(u64*)&b)); return d; }
 __device__ __forceinline__ float2 fsub2(float2 a, float2 b) { float2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(*(u64*)&d) : "l"(*(u64*)&a), "l"(*(u64*)&b)); return d; }
 __device__ __forceinline__ float2 fmul2(float2 a, float2 b) { float2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(*(u64*)&d) : "l"(*(u64*)&a), "l"(*(u64*)&b)); return d; }
 __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }

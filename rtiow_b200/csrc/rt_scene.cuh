@@ -2,7 +2,7 @@
 // /root/reference/src/shapes/mod.rs:56-69) of the B200 render path.
 //
 // Layout in HBM (built once by rtiow_scene_upload, read-only afterwards):
-//   soa      float [4][np]   cx | cy | cz | r2f   "small" spheres in list order, padded to a multiple
+//   soa      float [4][np]   cx | cy | cz | K     "small" spheres in list order, padded to a multiple
 //                            of 32 with never-hit entries; staged into shared memory by each CTA and
 //                            streamed as broadcast LDS.128 (4 spheres per load per array)
 //   small    float4 [np]     (cx, cy, cz, r) exact f32 copy for the precise test of candidates
@@ -34,9 +34,11 @@ struct SceneDev {
 };
 
 #define RT_FULL 0xffffffffu
-// d' = d * (1 + 2^-21): the filter sees half_b^2 inflated by ~2^-20, four times the worst-case f32
-// rounding of the filter expression, so every sphere the precise test can accept passes the filter.
-#define RT_FILTER_DIR_SCALE 1.000000476837158203125f
+// Conservative slack of the f32 filter, in units of (|c|^2 + |o|^2): 96 * 2^-24.  The filter's rounding
+// error is bounded by ~40 u (|c|^2 + |o|^2) + 4 u r^2 (u = 2^-24; derivation in DESIGN.md), so with this
+// slack every sphere the precise test can accept passes the filter.  The per-sphere share is folded
+// into K at upload, the per-ray share into |o|^2 below: no cost inside the loop.
+#define RT_FILTER_SLACK 5.7220458984375e-06f
 #define RT_CAND_CAP 16           // candidate slots per lane per segment (uint16 positions)
 #define RT_SEG_WORDS 32          // 32 words x 32 spheres per segment between drains
 
@@ -51,13 +53,13 @@ struct HitF {           // closest hit so far; t in units of the normalised dire
 // The reference scans in list order and accepts root <= closest_so_far, so among equal roots the
 // LARGEST index wins (sphere.rs:29,31; mod.rs:61-66); `t < best || (t == best && idx > best_idx)`
 // gives the same winner for any processing order.
-template <typename T>
+template <typename T, bool kSeededSqrt = false>
 __device__ __forceinline__ void candidate(V3<T> o, V3<T> dhat, T inv_a, T t_min, V3<T> c, T r, int idx, T* t_best, int* i_best)
 {
     T t;
     // t_max = +inf: a root beyond the current closest is rejected by the comparison below, exactly
     // as sphere.rs:29-33 rejects it (its far root is farther still)
-    if (!sphere_roots(c - o, dhat, inv_a, r * r, t_min, (T)__int_as_float(0x7f800000), &t)) return;
+    if (!sphere_roots<T, kSeededSqrt>(c - o, dhat, inv_a, r * r, t_min, (T)__int_as_float(0x7f800000), &t)) return;
     if (t < *t_best || (t == *t_best && idx > *i_best)) { *t_best = t; *i_best = idx; }
 }
 
@@ -76,10 +78,13 @@ __device__ __forceinline__ void candidate_self(V3<T> dhat, T inv_a, T t_min, V3<
 }
 
 // The f32 scan over the shared-memory SoA.
-//   filter (all spheres, branch-free, packed f32x2 over sphere pairs):
-//       oc = c - o;  hb = oc . d';  disc' = hb^2 - |oc|^2 + r2f        (10 packed ops per 2 tests)
-//     disc' >= 0 is a conservative superset of "discriminant >= 0" (sphere.rs:24-25); its sign bit is
-//     funnel-shifted into a 32-sphere word (1 SHF per test on the ALU pipe, co-issued).
+//   filter (all spheres, branch-free, packed f32x2 over sphere pairs), sphere.rs:18-25 expanded around
+//   the coordinate origin so that the per-ray and per-sphere parts separate:
+//       hb = c.d - o.d ;  C = K + |o|^2 - 2 c.o ,  K = |c|^2 - r^2 ;  disc' = hb^2 - C     (8 packed ops per 2 tests)
+//     With K and |o|^2 lowered by RT_FILTER_SLACK, disc' >= 0 is a conservative superset of
+//     "discriminant >= 0" (sphere.rs:24-25); its sign bit is funnel-shifted into a 32-sphere word
+//     (1 SHF per test on the ALU pipe, co-issued).  The expansion cancels |c|^2 + |o|^2 against 2 c.o, which
+//     is why it is only a filter: every survivor goes through the well-conditioned sphere_roots.
 //   candidates (a few per ray): positions appended to a per-lane list in shared memory, then the
 //     whole warp drains its lists in lock-step through candidate<float>.
 // s_soa: [4][np] floats in shared memory (or global when the scene does not fit).
@@ -92,31 +97,42 @@ __device__ __forceinline__ void scan_small(const float* __restrict__ s_soa, int 
     const float4* CX = reinterpret_cast<const float4*>(s_soa);
     const float4* CY = CX + n4;
     const float4* CZ = CY + n4;
-    const float4* RR = CZ + n4;
-    const float2 OX = bc2(o.x), OY = bc2(o.y), OZ = bc2(o.z);
-    const float2 DX = bc2(dhat.x * RT_FILTER_DIR_SCALE), DY = bc2(dhat.y * RT_FILTER_DIR_SCALE), DZ = bc2(dhat.z * RT_FILTER_DIR_SCALE);
+    const float4* KK = CZ + n4;
+    const float oo = length_squared(o);
+    const float2 M2OX = bc2(-2.0f * o.x), M2OY = bc2(-2.0f * o.y), M2OZ = bc2(-2.0f * o.z);
+    const float2 DX = bc2(dhat.x), DY = bc2(dhat.y), DZ = bc2(dhat.z);
+    const float2 NOD = bc2(-dot(o, dhat));
+    const float2 OO = bc2(oo - RT_FILTER_SLACK * oo);
     const int n_words = np >> 5;
     int pb = *p_best; float tb = *t_best;
+    // the sphere the ray starts on is tested on its own, independently of the filter
+    if (self_pos >= 0) candidate_self<float>(dhat, inv_a, t_min, self_n, small[self_pos].w, self_pos, &tb, &pb);
 
+    // software pipeline: the quad (4 spheres x 4 arrays, 4 LDS.128) for step q+1 is loaded while step q
+    // computes, so the ~30-cycle shared-memory latency hides behind 16 FFMA2 of the same warp
+    if (n_words == 0) { *p_best = pb; *t_best = tb; return; }
+    float4 ncx = CX[0], ncy = CY[0], ncz = CZ[0], nkk = KK[0];
     for (int w0 = 0; w0 < n_words; w0 += RT_SEG_WORDS) {
         const int w1 = min(w0 + RT_SEG_WORDS, n_words);
         int nc = 0;
         for (int w = w0; w < w1; ++w) {
             unsigned m = 0;
             const int q0 = w << 3;
+            const int q_next_word = (w + 1 < n_words) ? q0 + 8 : q0;     // the last word re-reads its first quad (unused)
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                const float4 cx = CX[q0 + q], cy = CY[q0 + q], cz = CZ[q0 + q], rr = RR[q0 + q];
+                const float4 cx = ncx, cy = ncy, cz = ncz, kk = nkk;
+                const int qn = q < 7 ? q0 + q + 1 : q_next_word;
+                ncx = CX[qn]; ncy = CY[qn]; ncz = CZ[qn]; nkk = KK[qn];
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const float2 X = h ? make_float2(cx.z, cx.w) : make_float2(cx.x, cx.y);
                     const float2 Y = h ? make_float2(cy.z, cy.w) : make_float2(cy.x, cy.y);
                     const float2 Z = h ? make_float2(cz.z, cz.w) : make_float2(cz.x, cz.y);
-                    const float2 Q = h ? make_float2(rr.z, rr.w) : make_float2(rr.x, rr.y);
-                    const float2 ocx = fsub2(X, OX), ocy = fsub2(Y, OY), ocz = fsub2(Z, OZ);
-                    const float2 hb = ffma2(ocz, DZ, ffma2(ocy, DY, fmul2(ocx, DX)));
-                    const float2 nc2 = ffma2(neg2(ocx), ocx, ffma2(neg2(ocy), ocy, ffma2(neg2(ocz), ocz, Q)));
-                    const float2 disc = ffma2(hb, hb, nc2);
+                    const float2 K = h ? make_float2(kk.z, kk.w) : make_float2(kk.x, kk.y);
+                    const float2 hb = ffma2(X, DX, ffma2(Y, DY, ffma2(Z, DZ, NOD)));
+                    const float2 C = ffma2(X, M2OX, ffma2(Y, M2OY, ffma2(Z, M2OZ, fadd2(K, OO))));
+                    const float2 disc = ffma2(hb, hb, neg2(C));
                     m = __funnelshift_l(__float_as_uint(disc.x), m, 1);
                     m = __funnelshift_l(__float_as_uint(disc.y), m, 1);
                 }
@@ -127,20 +143,14 @@ __device__ __forceinline__ void scan_small(const float* __restrict__ s_soa, int 
                 c &= ~(0x80000000u >> k);
                 const int p = (w << 5) + k;
                 if (nc < RT_CAND_CAP) { cand[nc * cand_stride] = (uint16_t)(p - (w0 << 5)); ++nc; }
-                else {
-                    const float4 s = small[p];
-                    if (p == self_pos) candidate_self<float>(dhat, inv_a, t_min, self_n, s.w, p, &tb, &pb);
-                    else candidate<float>(o, dhat, inv_a, t_min, mk(s.x, s.y, s.z), s.w, p, &tb, &pb);
-                }
+                else if (p != self_pos) { const float4 s = small[p]; candidate<float>(o, dhat, inv_a, t_min, mk(s.x, s.y, s.z), s.w, p, &tb, &pb); }
             }
         }
         const int nmax = __reduce_max_sync(RT_FULL, nc);
         for (int k = 0; k < nmax; ++k) {
             if (k < nc) {
                 const int p = (w0 << 5) + cand[k * cand_stride];
-                const float4 s = small[p];
-                if (p == self_pos) candidate_self<float>(dhat, inv_a, t_min, self_n, s.w, p, &tb, &pb);
-                else candidate<float>(o, dhat, inv_a, t_min, mk(s.x, s.y, s.z), s.w, p, &tb, &pb);
+                if (p != self_pos) { const float4 s = small[p]; candidate<float>(o, dhat, inv_a, t_min, mk(s.x, s.y, s.z), s.w, p, &tb, &pb); }
             }
         }
     }
@@ -162,7 +172,7 @@ __device__ __forceinline__ HitF closest_hit(const SceneDev& sc, const float* s_s
     HitF h; h.t = tb; h.idx = pb >= 0 ? sc.small_idx[pb] : -1; h.code = pb;
     if (sc.nb > 0) {
         const V3<double> od = mk<double>(o.x, o.y, o.z), dd = mk<double>(dhat.x, dhat.y, dhat.z);
-        const double inv_ad = 1.0 / length_squared(dd);
+        const double inv_ad = 2.0 - length_squared(dd);          // 1/a for a = 1 + e, |e| < 1e-6: exact to e^2
         double tbd = (double)h.t; int ib = h.idx;
         for (int b = 0; b < sc.nb; ++b) {
             const double4 s = sc.big[b];
@@ -172,7 +182,7 @@ __device__ __forceinline__ HitF closest_hit(const SceneDev& sc, const float* s_s
                 sn = sn * (1.0 / sqrt(length_squared(sn)));
                 candidate_self<double>(dd, inv_ad, (double)t_min, sn, s.w, sc.big_idx[b], &tbd, &ib);
             } else {
-                candidate<double>(od, dd, inv_ad, (double)t_min, mk(s.x, s.y, s.z), s.w, sc.big_idx[b], &tbd, &ib);
+                candidate<double, true>(od, dd, inv_ad, (double)t_min, mk(s.x, s.y, s.z), s.w, sc.big_idx[b], &tbd, &ib);
             }
             if (ib != before || tbd != tbefore) { h.idx = ib; h.t = (float)tbd; h.code = -2 - b; }
         }

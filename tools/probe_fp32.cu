@@ -191,6 +191,167 @@ __global__ void __launch_bounds__(256) k_scan_const(float* out, int n, int iters
   out[blockIdx.x*blockDim.x+threadIdx.x]=acc;
 }
 
+
+// ---- E3: 8-op expanded filter: hb = c.d - o.d ; C = K + |o|^2 - 2 c.o ; disc = hb^2 - C ---------------
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b){ float2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(*(u64*)&d) : "l"(*(u64*)&a), "l"(*(u64*)&b)); return d; }
+template<int R>
+__global__ void __launch_bounds__(256) k_scan_smem8(const float* __restrict__ g, float* out, int n, int iters){
+  extern __shared__ float4 sm4[];
+  const int n4=n/4;
+  for(int i=threadIdx.x;i<n;i+=blockDim.x) ((float*)sm4)[i]=g[i];
+  __syncthreads();
+  const float4* CX=sm4; const float4* CY=sm4+n4; const float4* CZ=sm4+2*n4; const float4* KK=sm4+3*n4;
+  float m2ox[R],m2oy[R],m2oz[R],dx[R],dy[R],dz[R],nod[R],oo[R]; unsigned acc[R];
+  #pragma unroll
+  for(int r=0;r<R;r++){ float t=(threadIdx.x*R+r)*0.01f; float ox=13+t, oy=2, oz=3-t; dx[r]=-0.9f+t*1e-3f; dy[r]=-0.1f+t*0.01f; dz[r]=-0.2f-t*1e-3f;
+     m2ox[r]=-2*ox; m2oy[r]=-2*oy; m2oz[r]=-2*oz; nod[r]=-(ox*dx[r]+oy*dy[r]+oz*dz[r]); oo[r]=ox*ox+oy*oy+oz*oz; acc[r]=0; }
+  for(int it=0; it<iters; ++it){
+    for(int w=0; w<n4; w+=8){
+      unsigned m[R];
+      #pragma unroll
+      for(int r=0;r<R;r++) m[r]=0;
+      #pragma unroll
+      for(int q=0;q<8;q++){
+        float4 cx=CX[w+q], cy=CY[w+q], cz=CZ[w+q], kk=KK[w+q];
+        #pragma unroll
+        for(int h=0;h<2;h++){
+          float2 X= h? make_float2(cx.z,cx.w):make_float2(cx.x,cx.y);
+          float2 Y= h? make_float2(cy.z,cy.w):make_float2(cy.x,cy.y);
+          float2 Z= h? make_float2(cz.z,cz.w):make_float2(cz.x,cz.y);
+          float2 K= h? make_float2(kk.z,kk.w):make_float2(kk.x,kk.y);
+          #pragma unroll
+          for(int r=0;r<R;r++){
+            float2 hb=ffma2(X,bc(dx[r]),ffma2(Y,bc(dy[r]),ffma2(Z,bc(dz[r]),bc(nod[r]))));
+            float2 C=ffma2(X,bc(m2ox[r]),ffma2(Y,bc(m2oy[r]),ffma2(Z,bc(m2oz[r]),fadd2(K,bc(oo[r])))));
+            float2 disc=ffma2(hb,hb,neg2(C));
+            m[r]=__funnelshift_l(__float_as_uint(disc.x), m[r], 1);
+            m[r]=__funnelshift_l(__float_as_uint(disc.y), m[r], 1);
+          }
+        }
+      }
+      #pragma unroll
+      for(int r=0;r<R;r++){ acc[r]+=__popc(~m[r]); oo[r]+=1e-6f; }
+    }
+  }
+  unsigned s=0;
+  #pragma unroll
+  for(int r=0;r<R;r++) s+=acc[r];
+  out[blockIdx.x*blockDim.x+threadIdx.x]=s;
+}
+
+// ---- E4: 8-op filter with explicit software prefetch of the next sphere quads (register double-buffering) ----
+template<int PF>
+__global__ void __launch_bounds__(256,3) k_scan_smem8_pf(const float* __restrict__ g, float* out, int n, int iters){
+  extern __shared__ float4 sm4[];
+  const int n4=n/4;
+  for(int i=threadIdx.x;i<n;i+=blockDim.x) ((float*)sm4)[i]=g[i];
+  __syncthreads();
+  const float4* CX=sm4; const float4* CY=sm4+n4; const float4* CZ=sm4+2*n4; const float4* KK=sm4+3*n4;
+  float t=(threadIdx.x)*0.01f; float ox=13+t, oy=2, oz=3-t; float dx=-0.9f+t*1e-3f, dy=-0.1f+t*0.01f, dz=-0.2f-t*1e-3f;
+  float m2ox=-2*ox, m2oy=-2*oy, m2oz=-2*oz, nod=-(ox*dx+oy*dy+oz*dz), oo=ox*ox+oy*oy+oz*oz; unsigned acc=0;
+  for(int it=0; it<iters; ++it){
+    float4 bx[PF+1],by[PF+1],bz[PF+1],bk[PF+1];
+    #pragma unroll
+    for(int p=0;p<PF;p++){ bx[p]=CX[p]; by[p]=CY[p]; bz[p]=CZ[p]; bk[p]=KK[p]; }
+    for(int w=0; w<n4; w+=8){
+      unsigned m=0;
+      #pragma unroll
+      for(int q=0;q<8;q++){
+        // prefetch quad (w+q+PF) into slot (q+PF)%(PF+1); wraps harmlessly at the end (index clamped)
+        int nx = w+q+PF; nx = nx < n4 ? nx : n4-1;
+        bx[(q+PF)%(PF+1)]=CX[nx]; by[(q+PF)%(PF+1)]=CY[nx]; bz[(q+PF)%(PF+1)]=CZ[nx]; bk[(q+PF)%(PF+1)]=KK[nx];
+        float4 cx=bx[q%(PF+1)], cy=by[q%(PF+1)], cz=bz[q%(PF+1)], kk=bk[q%(PF+1)];
+        #pragma unroll
+        for(int h=0;h<2;h++){
+          float2 X= h? make_float2(cx.z,cx.w):make_float2(cx.x,cx.y);
+          float2 Y= h? make_float2(cy.z,cy.w):make_float2(cy.x,cy.y);
+          float2 Z= h? make_float2(cz.z,cz.w):make_float2(cz.x,cz.y);
+          float2 K= h? make_float2(kk.z,kk.w):make_float2(kk.x,kk.y);
+          float2 hb=ffma2(X,bc(dx),ffma2(Y,bc(dy),ffma2(Z,bc(dz),bc(nod))));
+          float2 C=ffma2(X,bc(m2ox),ffma2(Y,bc(m2oy),ffma2(Z,bc(m2oz),fadd2(K,bc(oo)))));
+          float2 disc=ffma2(hb,hb,neg2(C));
+          m=__funnelshift_l(__float_as_uint(disc.x), m, 1);
+          m=__funnelshift_l(__float_as_uint(disc.y), m, 1);
+        }
+      }
+      acc+=__popc(~m); oo+=1e-6f;
+    }
+  }
+  out[blockIdx.x*blockDim.x+threadIdx.x]=acc;
+}
+
+// ---- E5: ablations of the 8-op scan: MODE 0 = full, 1 = no SHF (xor-accumulate one in 8 results), 2 = no LDS (sphere quads held in registers), 3 = neither
+template<int MODE>
+__global__ void __launch_bounds__(256) k_scan8_abl(const float* __restrict__ g, float* out, int n, int iters){
+  extern __shared__ float4 sm4[];
+  const int n4=n/4;
+  for(int i=threadIdx.x;i<n;i+=blockDim.x) ((float*)sm4)[i]=g[i];
+  __syncthreads();
+  const float4* CX=sm4; const float4* CY=sm4+n4; const float4* CZ=sm4+2*n4; const float4* KK=sm4+3*n4;
+  float t=(threadIdx.x)*0.01f; float ox=13+t, oy=2, oz=3-t; float dx=-0.9f+t*1e-3f, dy=-0.1f+t*0.01f, dz=-0.2f-t*1e-3f;
+  float m2ox=-2*ox, m2oy=-2*oy, m2oz=-2*oz, nod=-(ox*dx+oy*dy+oz*dz), oo=ox*ox+oy*oy+oz*oz; unsigned acc=0;
+  float4 rx=CX[threadIdx.x&7], ry=CY[threadIdx.x&7], rz=CZ[threadIdx.x&7], rk=KK[threadIdx.x&7];
+  for(int it=0; it<iters; ++it){
+    for(int w=0; w<n4; w+=8){
+      unsigned m=0;
+      #pragma unroll
+      for(int q=0;q<8;q++){
+        float4 cx,cy,cz,kk;
+        if (MODE&2) { cx=rx; cy=ry; cz=rz; kk=rk; rx.x+=1e-7f; } else { cx=CX[w+q]; cy=CY[w+q]; cz=CZ[w+q]; kk=KK[w+q]; }
+        #pragma unroll
+        for(int h=0;h<2;h++){
+          float2 X= h? make_float2(cx.z,cx.w):make_float2(cx.x,cx.y);
+          float2 Y= h? make_float2(cy.z,cy.w):make_float2(cy.x,cy.y);
+          float2 Z= h? make_float2(cz.z,cz.w):make_float2(cz.x,cz.y);
+          float2 K= h? make_float2(kk.z,kk.w):make_float2(kk.x,kk.y);
+          float2 hb=ffma2(X,bc(dx),ffma2(Y,bc(dy),ffma2(Z,bc(dz),bc(nod))));
+          float2 C=ffma2(X,bc(m2ox),ffma2(Y,bc(m2oy),ffma2(Z,bc(m2oz),fadd2(K,bc(oo)))));
+          float2 disc=ffma2(hb,hb,neg2(C));
+          if (MODE&1) { if (h==1 && (q&3)==3) m^=__float_as_uint(disc.x)^__float_as_uint(disc.y); else { oo+=disc.x*0.f; } }
+          else { m=__funnelshift_l(__float_as_uint(disc.x), m, 1); m=__funnelshift_l(__float_as_uint(disc.y), m, 1); }
+        }
+      }
+      acc+=__popc(~m); oo+=1e-6f;
+    }
+  }
+  out[blockIdx.x*blockDim.x+threadIdx.x]=acc;
+}
+
+// ---- E6: the 8-op scan with NO shared-memory loads: sphere quads live in registers and are perturbed with one
+//      LOP3 per register per use so that nothing is loop-invariant.  Isolates the LDS cost.
+__global__ void __launch_bounds__(256) k_scan8_regs(const float* __restrict__ g, float* out, int n, int iters){
+  const int n4=n/4;
+  float t=(threadIdx.x)*0.01f; float ox=13+t, oy=2, oz=3-t; float dx=-0.9f+t*1e-3f, dy=-0.1f+t*0.01f, dz=-0.2f-t*1e-3f;
+  float m2ox=-2*ox, m2oy=-2*oy, m2oz=-2*oz, nod=-(ox*dx+oy*dy+oz*dz), oo=ox*ox+oy*oy+oz*oz; unsigned acc=0;
+  const float4* G=(const float4*)g;
+  float4 rx=G[threadIdx.x&7], ry=G[n4+(threadIdx.x&7)], rz=G[2*n4+(threadIdx.x&7)], rk=G[3*n4+(threadIdx.x&7)];
+  for(int it=0; it<iters; ++it){
+    for(int w=0; w<n4; w+=8){
+      unsigned m=0;
+      #pragma unroll
+      for(int q=0;q<8;q++){
+        unsigned j=(unsigned)(w+q)&3u;     // flips low mantissa bits only
+        float4 cx=make_float4(__uint_as_float(__float_as_uint(rx.x)^j),__uint_as_float(__float_as_uint(rx.y)^j),__uint_as_float(__float_as_uint(rx.z)^j),__uint_as_float(__float_as_uint(rx.w)^j));
+        float4 cy=make_float4(__uint_as_float(__float_as_uint(ry.x)^j),__uint_as_float(__float_as_uint(ry.y)^j),__uint_as_float(__float_as_uint(ry.z)^j),__uint_as_float(__float_as_uint(ry.w)^j));
+        float4 cz=make_float4(__uint_as_float(__float_as_uint(rz.x)^j),__uint_as_float(__float_as_uint(rz.y)^j),__uint_as_float(__float_as_uint(rz.z)^j),__uint_as_float(__float_as_uint(rz.w)^j));
+        float4 kk=make_float4(__uint_as_float(__float_as_uint(rk.x)^j),__uint_as_float(__float_as_uint(rk.y)^j),__uint_as_float(__float_as_uint(rk.z)^j),__uint_as_float(__float_as_uint(rk.w)^j));
+        #pragma unroll
+        for(int h=0;h<2;h++){
+          float2 X= h? make_float2(cx.z,cx.w):make_float2(cx.x,cx.y);
+          float2 Y= h? make_float2(cy.z,cy.w):make_float2(cy.x,cy.y);
+          float2 Z= h? make_float2(cz.z,cz.w):make_float2(cz.x,cz.y);
+          float2 K= h? make_float2(kk.z,kk.w):make_float2(kk.x,kk.y);
+          float2 hb=ffma2(X,bc(dx),ffma2(Y,bc(dy),ffma2(Z,bc(dz),bc(nod))));
+          float2 C=ffma2(X,bc(m2ox),ffma2(Y,bc(m2oy),ffma2(Z,bc(m2oz),fadd2(K,bc(oo)))));
+          float2 disc=ffma2(hb,hb,neg2(C));
+          m=__funnelshift_l(__float_as_uint(disc.x), m, 1); m=__funnelshift_l(__float_as_uint(disc.y), m, 1);
+        }
+      }
+      acc+=__popc(~m); oo+=1e-6f;
+    }
+  }
+  out[blockIdx.x*blockDim.x+threadIdx.x]=acc;
+}
 static float time_ms(cudaEvent_t a, cudaEvent_t b){ float ms; CK(cudaEventElapsedTime(&ms,a,b)); return ms; }
 
 int main(int argc, char** argv){
@@ -229,6 +390,27 @@ int main(int argc, char** argv){
   SCAN("scan_smem_packed_R1",(k_scan_smem<1><<<ctas,threads,smem>>>(g,out,n,sit)),1);
   SCAN("scan_smem_packed_R2",(k_scan_smem<2><<<ctas,threads,smem>>>(g,out,n,sit)),2);
   SCAN("scan_smem_packed_R4",(k_scan_smem<4><<<ctas,threads,smem>>>(g,out,n,sit)),4);
+  SCAN("scan_smem8_packed_R1",(k_scan_smem8<1><<<ctas,threads,smem>>>(g,out,n,sit)),1);
+  SCAN("scan_smem8_packed_R2",(k_scan_smem8<2><<<ctas,threads,smem>>>(g,out,n,sit)),2);
+  SCAN("scan_smem8_packed_R4",(k_scan_smem8<4><<<ctas,threads,smem>>>(g,out,n,sit)),4);
+  SCAN("scan8_abl_full",(k_scan8_abl<0><<<ctas,threads,smem>>>(g,out,n,sit)),1);
+  SCAN("scan8_abl_noshf",(k_scan8_abl<1><<<ctas,threads,smem>>>(g,out,n,sit)),1);
+  SCAN("scan8_abl_nolds",(k_scan8_abl<2><<<ctas,threads,smem>>>(g,out,n,sit)),1);
+  SCAN("scan8_abl_neither",(k_scan8_abl<3><<<ctas,threads,smem>>>(g,out,n,sit)),1);
+  SCAN("scan8_regs_nolds",(k_scan8_regs<<<ctas,threads>>>(g,out,n,sit)),1);
+  SCAN("scan8_pf1",(k_scan_smem8_pf<1><<<ctas,threads,smem>>>(g,out,n,sit)),1);
+  SCAN("scan8_pf2",(k_scan_smem8_pf<2><<<ctas,threads,smem>>>(g,out,n,sit)),1);
+  SCAN("scan8_pf3",(k_scan_smem8_pf<3><<<ctas,threads,smem>>>(g,out,n,sit)),1);
+  // occupancy sweep of the 8-op scan: pad dynamic shared memory so that only `occ` CTAs (8 warps each) fit per SM
+  for (int occ = 8; occ >= 8; --occ) {
+    size_t pad = (size_t)(227 * 1024) / occ - 1024; if (pad < smem) pad = smem; if (pad > 200 * 1024) pad = 200 * 1024;
+    CK(cudaFuncSetAttribute(k_scan_smem8<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad));
+    CK(cudaFuncSetAttribute(k_scan_smem8<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad));
+    char nm[64]; snprintf(nm, sizeof nm, "scan8_R1_occ%d", occ);
+    SCAN(nm,(k_scan_smem8<1><<<ctas,threads,pad>>>(g,out,n,sit)),1);
+    snprintf(nm, sizeof nm, "scan8_R2_occ%d", occ);
+    SCAN(nm,(k_scan_smem8<2><<<ctas,threads,pad>>>(g,out,n,sit)),2);
+  }
   SCAN("scan_smem_scalar_R1",(k_scan_smem_scalar<1><<<ctas,threads,smem>>>(g,out,n,sit)),1);
   SCAN("scan_smem_scalar_R2",(k_scan_smem_scalar<2><<<ctas,threads,smem>>>(g,out,n,sit)),2);
   SCAN("scan_smem_scalar_R4",(k_scan_smem_scalar<4><<<ctas,threads,smem>>>(g,out,n,sit)),4);
