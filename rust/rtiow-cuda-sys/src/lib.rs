@@ -1,0 +1,114 @@
+//! Raw bindings to `include/rtiow_cuda.h` (ABI version 1).  One `extern "C"` item per exported symbol, one
+//! `#[repr(C)]` struct per C struct; layouts are asserted in `tests/test_host_cabi.py::test_struct_layouts_match_header`
+//! (Camera 176 B, Params 48 B, Stats 64 B, Spheres/Materials 48 B).
+//!
+//! NOT compiled in this repository's build container (no rustc); kept in lock-step with the header by review.
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int, c_void};
+
+pub const RTIOW_ABI_VERSION: c_int = 1;
+
+pub const RTIOW_OK: c_int = 0;
+pub const RTIOW_ERR_INVALID_ARG: c_int = -1;
+pub const RTIOW_ERR_UNSUPPORTED: c_int = -2;
+pub const RTIOW_ERR_CUDA: c_int = -3;
+pub const RTIOW_ERR_NCCL: c_int = -4;
+pub const RTIOW_ERR_NO_DEVICE: c_int = -5;
+pub const RTIOW_ERR_NOMEM: c_int = -6;
+
+pub const RTIOW_MAT_LAMBERTIAN: u32 = 0;
+pub const RTIOW_MAT_METAL: u32 = 1;
+pub const RTIOW_MAT_DIELECTRIC: u32 = 2;
+
+pub const RTIOW_PRECISION_F32: u8 = 0;
+pub const RTIOW_PRECISION_F64: u8 = 1;
+
+#[repr(C)]
+pub struct rtiow_ctx { _private: [u8; 0] }
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct rtiow_spheres {
+    pub cx: *const f64, pub cy: *const f64, pub cz: *const f64,
+    pub radius: *const f64,
+    pub mat_index: *const u32,
+    pub n: u32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct rtiow_materials {
+    pub kind: *const u32,
+    pub albedo_r: *const f64, pub albedo_g: *const f64, pub albedo_b: *const f64,
+    pub param: *const f64,
+    pub n: u32,
+}
+
+/// The 8 private fields of `Camera` (camera.rs:4-13).
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct rtiow_camera {
+    pub origin: [f64; 3], pub lower_left_corner: [f64; 3], pub horizontal: [f64; 3], pub vertical: [f64; 3],
+    pub u: [f64; 3], pub v: [f64; 3], pub w: [f64; 3],
+    pub lens_radius: f64,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct rtiow_params {
+    pub width: u32, pub height: u32, pub spp: u32,
+    pub max_depth: i32,
+    pub t_min: f64,
+    pub seed: u64,
+    pub alpha: u8, pub precision: u8, pub reserved: [u8; 6],
+    pub tile_rows: u32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct rtiow_stats {
+    pub kernel_ms: f64, pub total_ms: f64,
+    pub paths: u64, pub rays_traced: u64, pub sphere_tests: u64, pub h2d_bytes: u64, pub d2h_bytes: u64,
+    pub kernel_launches: u32, pub n_gpus: u32,
+}
+
+extern "C" {
+    pub fn rtiow_abi_version() -> c_int;
+    pub fn rtiow_last_error() -> *const c_char;
+    pub fn rtiow_device_count(out_count: *mut c_int) -> c_int;
+    pub fn rtiow_ctx_create(n_gpus: c_int, out: *mut *mut rtiow_ctx) -> c_int;
+    pub fn rtiow_ctx_create_on_device(device: c_int, out: *mut *mut rtiow_ctx) -> c_int;
+    pub fn rtiow_ctx_destroy(ctx: *mut rtiow_ctx);
+    pub fn rtiow_scene_upload(ctx: *mut rtiow_ctx, spheres: *const rtiow_spheres, materials: *const rtiow_materials) -> c_int;
+    pub fn rtiow_camera_new(look_from: *const f64, look_at: *const f64, v_up: *const f64, v_fov_deg: f64, aspect_ratio: f64,
+                            aperture: f64, focus_dist: f64, out: *mut rtiow_camera) -> c_int;
+    pub fn rtiow_params_default(p: *mut rtiow_params);
+    pub fn rtiow_render(ctx: *mut rtiow_ctx, cam: *const rtiow_camera, p: *const rtiow_params, out_rgba: *mut u8,
+                        stats: *mut rtiow_stats) -> c_int;
+    pub fn rtiow_tile_buffer_bytes(p: *const rtiow_params, world: c_int, out_bytes: *mut usize) -> c_int;
+    pub fn rtiow_render_tiles_device(ctx: *mut rtiow_ctx, cam: *const rtiow_camera, p: *const rtiow_params, rank: c_int, world: c_int,
+                                     d_tiles: *mut c_void, stream: *mut c_void, stats: *mut rtiow_stats) -> c_int;
+    pub fn rtiow_deinterleave_device(ctx: *mut rtiow_ctx, d_gathered: *const c_void, p: *const rtiow_params, world: c_int,
+                                     d_frame: *mut c_void, stream: *mut c_void) -> c_int;
+    pub fn rtiow_sphere_hit_batch(ctx: *mut rtiow_ctx, precision: c_int, n: i64, center: *const f64, radius: *const f64, orig: *const f64,
+                                  dir: *const f64, t_min: *const f64, t_max: *const f64, hit: *mut i32, t: *mut f64, p: *mut f64,
+                                  normal: *mut f64, front_face: *mut i32) -> c_int;
+    pub fn rtiow_hitlist_batch(ctx: *mut rtiow_ctx, precision: c_int, n: i64, orig: *const f64, dir: *const f64, t_min: f64, hit: *mut i32,
+                               index: *mut i32, t: *mut f64, p: *mut f64, normal: *mut f64, front_face: *mut i32) -> c_int;
+    pub fn rtiow_scatter_batch(ctx: *mut rtiow_ctx, precision: c_int, n: i64, kind: *const i32, albedo: *const f64, param: *const f64,
+                               r_orig: *const f64, r_dir: *const f64, p: *const f64, normal: *const f64, front_face: *const i32,
+                               sample: *const f64, some: *mut i32, attenuation: *mut f64, s_orig: *mut f64, s_dir: *mut f64) -> c_int;
+    pub fn rtiow_get_ray_batch(ctx: *mut rtiow_ctx, precision: c_int, cam: *const rtiow_camera, n: i64, s: *const f64, t: *const f64,
+                               disk_xy: *const f64, orig: *mut f64, dir: *mut f64) -> c_int;
+    pub fn rtiow_to_rgba_batch(ctx: *mut rtiow_ctx, precision: c_int, n: i64, color: *const f64, alpha: u8, spp: u64, out_rgba: *mut u8) -> c_int;
+    pub fn rtiow_reflect_batch(ctx: *mut rtiow_ctx, precision: c_int, n: i64, v: *const f64, nrm: *const f64, out: *mut f64) -> c_int;
+    pub fn rtiow_refract_batch(ctx: *mut rtiow_ctx, precision: c_int, n: i64, uv: *const f64, nrm: *const f64, eta: *const f64, out: *mut f64) -> c_int;
+    pub fn rtiow_ray_color_batch(ctx: *mut rtiow_ctx, precision: c_int, n: i64, orig: *const f64, dir: *const f64, pixel: *const u32,
+                                 sample: *const u32, seed: u64, max_depth: i32, t_min: f64, color: *mut f64, rays: *mut u64) -> c_int;
+    pub fn rtiow_sampler_batch(ctx: *mut rtiow_ctx, precision: c_int, n: i64, pixel: *const u32, sample: *const u32, bounce: *const u32,
+                               seed: u64, out: *mut f64) -> c_int;
+    pub fn rtiow_fp32_peak_probe(ctx: *mut rtiow_ctx, packed: c_int, target_ms: f64, out_tflops: *mut f64, out_ms: *mut f64) -> c_int;
+    pub fn rtiow_flush_l2(ctx: *mut rtiow_ctx) -> c_int;
+    pub fn rtiow_random_scene(seed: u64, half_extent: i32, material_mode: i32, cap: u32, cx: *mut f64, cy: *mut f64, cz: *mut f64,
+                              radius: *mut f64, mat_kind: *mut u32, albedo_rgb: *mut f64, mat_param: *mut f64, out_n: *mut u32) -> c_int;
+}

@@ -1,0 +1,89 @@
+//! gpu.rs — drop this file into the reference crate as `src/gpu.rs` (`pub mod gpu;` in main.rs) together with the
+//! four small additions listed in INTEGRATION.md.  It adds ONE call, `gpu::render`, that replaces the rayon pixel loop,
+//! the collect and the row flip of main.rs:122-145 with the B200 backend.  Everything else in the crate is unchanged:
+//! `Hit::hit`, `Scatter::scatter` and `Camera::get_ray` keep working on the CPU for callers that use them directly,
+//! but `render` never falls back to them.
+//!
+//! NOT compiled in this repository's build container (no rustc/cargo there).
+use std::ffi::CStr;
+use std::ptr;
+
+use rtiow_cuda_sys as sys;
+
+use crate::camera::Camera;
+use crate::shapes::HittableList;
+
+/// What `Hit::describe` returns for a shape the GPU knows (only spheres exist in the reference, shapes/sphere.rs:9-13).
+pub struct SphereDesc { pub center: [f64; 3], pub radius: f64, pub mat: std::sync::Arc<dyn crate::materials::Scatter> }
+
+/// What `Scatter::describe` returns (materials.rs:9-11,34-37,64-66).  `param` = fuzz (Metal) or ir (Dialectric).
+#[derive(Clone, Copy)]
+pub struct MaterialDesc { pub kind: u32, pub albedo: [f64; 3], pub param: f64 }
+
+/// Runtime form of the compile-time constants main.rs:24-28,44,137.
+#[derive(Clone, Debug)]
+pub struct RenderParams {
+    pub width: u32, pub height: u32, pub spp: u32, pub max_depth: i32, pub t_min: f64,
+    pub seed: u64, pub n_gpus: i32, pub alpha: u8,
+}
+
+impl Default for RenderParams {
+    fn default() -> Self {       // IMAGE_WIDTH 200, 3:2 -> 133 rows, 100 spp, depth 50, t_min 0.0001, alpha 255
+        RenderParams { width: 200, height: 133, spp: 100, max_depth: 50, t_min: 0.0001, seed: 1, n_gpus: 1, alpha: 255 }
+    }
+}
+
+#[derive(Debug)]
+pub enum RenderError { InvalidArg(String), Unsupported(String), Cuda(String), Nccl(String), NoDevice(String), NoMem(String) }
+
+fn err(code: i32) -> RenderError {
+    let msg = unsafe { CStr::from_ptr(sys::rtiow_last_error()) }.to_string_lossy().into_owned();
+    match code {
+        sys::RTIOW_ERR_UNSUPPORTED => RenderError::Unsupported(msg),
+        sys::RTIOW_ERR_CUDA => RenderError::Cuda(msg),
+        sys::RTIOW_ERR_NCCL => RenderError::Nccl(msg),
+        sys::RTIOW_ERR_NO_DEVICE => RenderError::NoDevice(msg),
+        sys::RTIOW_ERR_NOMEM => RenderError::NoMem(msg),
+        _ => RenderError::InvalidArg(msg),
+    }
+}
+
+struct Ctx(*mut sys::rtiow_ctx);
+impl Drop for Ctx { fn drop(&mut self) { unsafe { sys::rtiow_ctx_destroy(self.0) } } }   // Send, !Sync: one caller per ctx
+
+/// Replaces main.rs:122-145.  Returns top-down RGBA8, `4*width*height` bytes: exactly the `Vec<u8>` handed to
+/// `ImageBuffer::from_vec(IMAGE_WIDTH, IMAGE_HEIGHT, pixels)` at main.rs:147.
+pub fn render(cam: &Camera, world: &HittableList, p: &RenderParams) -> Result<Vec<u8>, RenderError> {
+    // flatten the trait objects through the provided describe() methods; unknown ones are an error, not a CPU fallback
+    let (mut cx, mut cy, mut cz, mut radius, mut mat_index) = (vec![], vec![], vec![], vec![], vec![]);
+    let (mut kind, mut ar, mut ag, mut ab, mut param) = (vec![], vec![], vec![], vec![], vec![]);
+    let mut seen: Vec<*const ()> = vec![];
+    for shape in world.iter() {
+        let s = shape.describe().ok_or_else(|| RenderError::Unsupported("shape without a GPU description".into()))?;
+        let m = s.mat.describe().ok_or_else(|| RenderError::Unsupported("material without a GPU description".into()))?;
+        let key = std::sync::Arc::as_ptr(&s.mat) as *const ();
+        let id = match seen.iter().position(|k| *k == key) {
+            Some(i) => i,
+            None => { seen.push(key); kind.push(m.kind); ar.push(m.albedo[0]); ag.push(m.albedo[1]); ab.push(m.albedo[2]); param.push(m.param); seen.len() - 1 }
+        };
+        cx.push(s.center[0]); cy.push(s.center[1]); cz.push(s.center[2]); radius.push(s.radius); mat_index.push(id as u32);
+    }
+    unsafe {
+        let mut raw: *mut sys::rtiow_ctx = ptr::null_mut();
+        let rc = sys::rtiow_ctx_create(p.n_gpus, &mut raw);
+        if rc != sys::RTIOW_OK { return Err(err(rc)); }
+        let ctx = Ctx(raw);
+        let spheres = sys::rtiow_spheres { cx: cx.as_ptr(), cy: cy.as_ptr(), cz: cz.as_ptr(), radius: radius.as_ptr(), mat_index: mat_index.as_ptr(), n: radius.len() as u32 };
+        let mats = sys::rtiow_materials { kind: kind.as_ptr(), albedo_r: ar.as_ptr(), albedo_g: ag.as_ptr(), albedo_b: ab.as_ptr(), param: param.as_ptr(), n: kind.len() as u32 };
+        let rc = sys::rtiow_scene_upload(ctx.0, &spheres, &mats);
+        if rc != sys::RTIOW_OK { return Err(err(rc)); }
+        let mut prm: sys::rtiow_params = std::mem::zeroed();
+        sys::rtiow_params_default(&mut prm);
+        prm.width = p.width; prm.height = p.height; prm.spp = p.spp; prm.max_depth = p.max_depth; prm.t_min = p.t_min;
+        prm.seed = p.seed; prm.alpha = p.alpha;
+        let mut pixels = vec![0u8; 4 * p.width as usize * p.height as usize];
+        let rc = sys::rtiow_render(ctx.0, &cam.raw(), &prm, pixels.as_mut_ptr(), ptr::null_mut());
+        if rc != sys::RTIOW_OK { return Err(err(rc)); }
+        Ok(pixels)
+    }
+}
