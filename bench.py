@@ -36,6 +36,10 @@ WORKLOAD = dict(name="RTIOW Part 1 final scene (seeded random_scene), 1200x675, 
                 max_depth=50, t_min=1e-4, scene_seed=1, sample_seed=1)
 FLOP_PER_TEST = 17.0            # sphere.rs:18-25 with a and r^2 hoisted
 FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE render_kernel launch of this workload on one GPU, from the ncu --set full
+# capture summarised in profiles/r1_d_render_kernel_ncu_bench_size.txt (19.56 MB read + 256 B written): the scene, the
+# per-sphere records and the fixed-point accumulators; the 9.7 TFLOP of the launch run out of shared memory and registers.
+NCU_DRAM_BYTES_PER_LAUNCH = 19_560_448
 
 
 def parse():
@@ -282,7 +286,8 @@ def run_ours(args, rank, local_rank, world):
             "e2e": {"value": paths / (e2e_ms * 1e-3) / 1e6, "unit": "Mpaths/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": scene_bytes + 176 + 48, "d2h_bytes_per_step": W * H * 4 + 16},
             "gpu_launches": n_launch,
-            "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": None,
+            "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
+                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (world == 1 and (W, H, spp) == (1200, 675, 500)) else None, "traffic_unit": "bytes/launch (ncu)",
                          "kernel": "rt::render_kernel<float,true,256,3>", "kernel_ms": kms, "flop_per_test": FLOP_PER_TEST,
                          "rays_per_path": rays_total / paths, "sphere_tests_per_launch": rays_total * n_spheres / world,
                          "peak_source": "FFMA2 calibration kernel in this run (rtiow_fp32_peak_probe, ~300 ms); MEASURED_PEAKS.json has no FP32 entry",

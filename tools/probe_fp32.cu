@@ -352,6 +352,113 @@ __global__ void __launch_bounds__(256) k_scan8_regs(const float* __restrict__ g,
   }
   out[blockIdx.x*blockDim.x+threadIdx.x]=acc;
 }
+
+// ---- E7: 8-op scan, op-major order over NP sphere pairs (operand-reuse friendly: consecutive FFMA2 share the scalar operand)
+template<int NP>   // pairs per step: 2 (one quad), 4 (two quads)
+__global__ void __launch_bounds__(256,3) k_scan8_opmajor(const float* __restrict__ g, float* out, int n, int iters){
+  extern __shared__ float4 sm4[];
+  const int n4=n/4;
+  for(int i=threadIdx.x;i<n;i+=blockDim.x) ((float*)sm4)[i]=g[i];
+  __syncthreads();
+  const float4* CX=sm4; const float4* CY=sm4+n4; const float4* CZ=sm4+2*n4; const float4* KK=sm4+3*n4;
+  float t=(threadIdx.x)*0.01f; float ox=13+t, oy=2, oz=3-t; float dx=-0.9f+t*1e-3f, dy=-0.1f+t*0.01f, dz=-0.2f-t*1e-3f;
+  float m2ox=-2*ox, m2oy=-2*oy, m2oz=-2*oz, nod=-(ox*dx+oy*dy+oz*dz), oo=ox*ox+oy*oy+oz*oz; unsigned acc=0;
+  constexpr int NQ=NP/2;
+  for(int it=0; it<iters; ++it){
+    for(int w=0; w<n4; w+=8){
+      unsigned m=0;
+      #pragma unroll
+      for(int q=0;q<8;q+=NQ){
+        float2 X[NP],Y[NP],Z[NP],K[NP],hb[NP],C[NP];
+        #pragma unroll
+        for(int j=0;j<NQ;j++){ float4 cx=CX[w+q+j], cy=CY[w+q+j], cz=CZ[w+q+j], kk=KK[w+q+j];
+          X[2*j]=make_float2(cx.x,cx.y); X[2*j+1]=make_float2(cx.z,cx.w); Y[2*j]=make_float2(cy.x,cy.y); Y[2*j+1]=make_float2(cy.z,cy.w);
+          Z[2*j]=make_float2(cz.x,cz.y); Z[2*j+1]=make_float2(cz.z,cz.w); K[2*j]=make_float2(kk.x,kk.y); K[2*j+1]=make_float2(kk.z,kk.w); }
+        #pragma unroll
+        for(int p=0;p<NP;p++) C[p]=fadd2(K[p],bc(oo));
+        #pragma unroll
+        for(int p=0;p<NP;p++) hb[p]=ffma2(Z[p],bc(dz),bc(nod));
+        #pragma unroll
+        for(int p=0;p<NP;p++) C[p]=ffma2(Z[p],bc(m2oz),C[p]);
+        #pragma unroll
+        for(int p=0;p<NP;p++) hb[p]=ffma2(Y[p],bc(dy),hb[p]);
+        #pragma unroll
+        for(int p=0;p<NP;p++) C[p]=ffma2(Y[p],bc(m2oy),C[p]);
+        #pragma unroll
+        for(int p=0;p<NP;p++) hb[p]=ffma2(X[p],bc(dx),hb[p]);
+        #pragma unroll
+        for(int p=0;p<NP;p++) C[p]=ffma2(X[p],bc(m2ox),C[p]);
+        #pragma unroll
+        for(int p=0;p<NP;p++){ float2 disc=ffma2(hb[p],hb[p],neg2(C[p]));
+          m=__funnelshift_l(__float_as_uint(disc.x), m, 1); m=__funnelshift_l(__float_as_uint(disc.y), m, 1); }
+      }
+      acc+=__popc(~m); oo+=1e-6f;
+    }
+  }
+  out[blockIdx.x*blockDim.x+threadIdx.x]=acc;
+}
+
+// ---- F: FFMA2 operand-form probes (register-file bandwidth): acc[i] = fma(X[i], s, acc[i]) with
+//      FORM 0: X pair, s pair (same for all), acc pair      FORM 1: X pair, s scalar-broadcast (4 different), acc pair
+//      FORM 2: like 1 but the addend is a scalar-broadcast constant for half of the ops (as in the scan's chain heads)
+template<int FORM>
+__global__ void __launch_bounds__(256) k_ffma2_forms(float* out, int iters, float a, float b){
+  float2 X[8], acc[8]; float sc[4];
+  #pragma unroll
+  for(int i=0;i<8;i++){ X[i]=make_float2(threadIdx.x*0.001f+i, i*0.5f+a); acc[i]=make_float2(i*b, i+a); }
+  #pragma unroll
+  for(int i=0;i<4;i++) sc[i]=a*(i+1)+threadIdx.x*1e-6f;
+  float2 S=make_float2(a,a*1.5f);
+  for(int it=0; it<iters; ++it){
+    #pragma unroll
+    for(int r=0;r<8;r++){
+      #pragma unroll
+      for(int i=0;i<8;i++){
+        if (FORM==0) acc[i]=ffma2(X[i],S,acc[i]);
+        else if (FORM==1) acc[i]=ffma2(X[i],bc(sc[(i+r)&3]),acc[i]);
+        else { if ((i+r)&1) acc[i]=ffma2(X[i],bc(sc[(i+r)&3]),acc[i]); else acc[i]=ffma2(X[(i+1)&7],bc(sc[(i+r)&3]),ffma2(acc[i],bc(0.f),bc(sc[r&3]))); }
+      }
+    }
+    X[it&7].x+=1e-7f;
+  }
+  float s=0; for(int i=0;i<8;i++) s+=acc[i].x+acc[i].y;
+  out[blockIdx.x*blockDim.x+threadIdx.x]=s;
+}
+
+// ---- E8: 8-op scan, sphere scalars from the CONSTANT BANK (uniform registers), two rays per lane in the f32x2 halves.
+//      Every FFMA2 then has at most two register-file pair operands (the third is a uniform-register broadcast).
+template<int RP>
+__global__ void __launch_bounds__(256) k_scan8_const(float* out, int n, int iters){
+  float2 dx[RP],dy[RP],dz[RP],m2ox[RP],m2oy[RP],m2oz[RP],nod[RP],oo[RP]; unsigned acc=0;
+  #pragma unroll
+  for(int r=0;r<RP;r++){ float t=(threadIdx.x*RP+r)*0.01f; float2 ox=make_float2(13+t,13-t), oy=make_float2(2,2.1f), oz=make_float2(3-t,3+t);
+    dx[r]=make_float2(-0.9f+t*1e-3f,-0.9f-t*1e-3f); dy[r]=make_float2(-0.1f+t*0.01f,-0.1f); dz[r]=make_float2(-0.2f-t*1e-3f,-0.2f+t*1e-3f);
+    m2ox[r]=make_float2(-2*ox.x,-2*ox.y); m2oy[r]=make_float2(-2*oy.x,-2*oy.y); m2oz[r]=make_float2(-2*oz.x,-2*oz.y);
+    nod[r]=make_float2(-(ox.x*dx[r].x+oy.x*dy[r].x+oz.x*dz[r].x),-(ox.y*dx[r].y+oy.y*dy[r].y+oz.y*dz[r].y));
+    oo[r]=make_float2(ox.x*ox.x+oy.x*oy.x+oz.x*oz.x, ox.y*ox.y+oy.y*oy.y+oz.y*oz.y); }
+  for(int it=0; it<iters; ++it){
+    for(int w=0; w<n; w+=32){
+      unsigned m0[RP], m1[RP];
+      #pragma unroll
+      for(int r=0;r<RP;r++){ m0[r]=0; m1[r]=0; }
+      #pragma unroll
+      for(int q=0;q<32;q++){
+        float4 s=c_sph[w+q];     // (cx,cy,cz,K) warp-uniform
+        #pragma unroll
+        for(int r=0;r<RP;r++){
+          float2 hb=ffma2(bc(s.x),dx[r],ffma2(bc(s.y),dy[r],ffma2(bc(s.z),dz[r],nod[r])));
+          float2 C=ffma2(bc(s.x),m2ox[r],ffma2(bc(s.y),m2oy[r],ffma2(bc(s.z),m2oz[r],fadd2(bc(s.w),oo[r]))));
+          float2 disc=ffma2(hb,hb,neg2(C));
+          m0[r]=__funnelshift_l(__float_as_uint(disc.x), m0[r], 1);
+          m1[r]=__funnelshift_l(__float_as_uint(disc.y), m1[r], 1);
+        }
+      }
+      #pragma unroll
+      for(int r=0;r<RP;r++){ acc+=__popc(~m0[r])+__popc(~m1[r]); oo[r].x+=1e-6f; }
+    }
+  }
+  out[blockIdx.x*blockDim.x+threadIdx.x]=acc;
+}
 static float time_ms(cudaEvent_t a, cudaEvent_t b){ float ms; CK(cudaEventElapsedTime(&ms,a,b)); return ms; }
 
 int main(int argc, char** argv){
@@ -378,6 +485,8 @@ int main(int argc, char** argv){
   int iters=4096;
   RUN("ffma_scalar", (k_ffma<<<ctas,threads>>>(out,iters,1.0001f,0.5f)), 2.0*64*iters, "");
   RUN("ffma2_packed", (k_ffma2<<<ctas,threads>>>(out,iters,1.0001f,0.5f)), 4.0*64*iters, "");
+  RUN("ffma2_form0_pair_pair_pair", (k_ffma2_forms<0><<<ctas,threads>>>(out,iters,1.0001f,0.5f)), 4.0*64*iters, "");
+  RUN("ffma2_form1_pair_scalar_pair", (k_ffma2_forms<1><<<ctas,threads>>>(out,iters,1.0001f,0.5f)), 4.0*64*iters, "");
   RUN("ffma2_plus_shf", (k_ffma2_shf<<<ctas,threads>>>(out,iters,1.0001f,0.5f)), 4.0*64*iters, ",\"note\":\"1 SHF per 2 FFMA2\"");
   { int it=64; 
     for(int rep=0;rep<2;rep++) k_lds128<<<ctas,threads>>>(out,it); CK(cudaDeviceSynchronize());
@@ -398,6 +507,11 @@ int main(int argc, char** argv){
   SCAN("scan8_abl_nolds",(k_scan8_abl<2><<<ctas,threads,smem>>>(g,out,n,sit)),1);
   SCAN("scan8_abl_neither",(k_scan8_abl<3><<<ctas,threads,smem>>>(g,out,n,sit)),1);
   SCAN("scan8_regs_nolds",(k_scan8_regs<<<ctas,threads>>>(g,out,n,sit)),1);
+  SCAN("scan8_opmajor_2",(k_scan8_opmajor<2><<<ctas,threads,smem>>>(g,out,n,sit)),1);
+  SCAN("scan8_opmajor_4",(k_scan8_opmajor<4><<<ctas,threads,smem>>>(g,out,n,sit)),1);
+  SCAN("scan8_opmajor_8",(k_scan8_opmajor<8><<<ctas,threads,smem>>>(g,out,n,sit)),1);
+  SCAN("scan8_const_RP1",(k_scan8_const<1><<<ctas,threads>>>(out,n,sit)),2);
+  SCAN("scan8_const_RP2",(k_scan8_const<2><<<ctas,threads>>>(out,n,sit)),4);
   SCAN("scan8_pf1",(k_scan_smem8_pf<1><<<ctas,threads,smem>>>(g,out,n,sit)),1);
   SCAN("scan8_pf2",(k_scan_smem8_pf<2><<<ctas,threads,smem>>>(g,out,n,sit)),1);
   SCAN("scan8_pf3",(k_scan_smem8_pf<3><<<ctas,threads,smem>>>(g,out,n,sit)),1);
