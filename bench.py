@@ -31,6 +31,7 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's version banner must not land on stdout: ONE JSON line there
 
 WORKLOAD = dict(name="RTIOW Part 1 final scene (seeded random_scene), 1200x675, 500 spp, depth 50", width=1200, height=675, spp=500,
                 max_depth=50, t_min=1e-4, scene_seed=1, sample_seed=1)
@@ -51,7 +52,7 @@ def parse():
     ap.add_argument("--width", type=int, default=WORKLOAD["width"])
     ap.add_argument("--height", type=int, default=WORKLOAD["height"])
     ap.add_argument("--spp", type=int, default=WORKLOAD["spp"])
-    ap.add_argument("--tile-rows", type=int, default=4)
+    ap.add_argument("--tile-rows", type=int, default=1)
     ap.add_argument("--cpu-sample-spp", type=int, default=0, help="spp of the bounded CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()

@@ -279,7 +279,7 @@ extern "C" void rtiow_params_default(rtiow_params* p)
     p->width = 200; p->height = 133; p->spp = 100; p->max_depth = 50;     // main.rs:24-28 (200/1.5 truncates to 133)
     p->t_min = 0.0001;                                                    // main.rs:44
     p->seed = 1; p->alpha = 255;                                          // main.rs:137
-    p->precision = RTIOW_PRECISION_F32; p->tile_rows = 4;
+    p->precision = RTIOW_PRECISION_F32; p->tile_rows = 1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -347,6 +347,7 @@ static int launch_render(DeviceState& d, const rtiow_camera* cam, const rtiow_pa
     RenderArgs<T> a;
     a.scene = d.scene; a.cam = to_dev_camera<T>(*cam);
     a.width = p->width; a.height = p->height; a.spp = p->spp; a.max_depth = p->max_depth; a.t_min = (T)p->t_min; a.seed = p->seed;
+    a.inv_wm1 = (T)(1.0 / (double)(p->width - 1)); a.inv_hm1 = (T)(1.0 / (double)(p->height - 1));
     a.rank = rank; a.world = world; a.tile_rows = p->tile_rows; a.local_rows = rows_of_rank(p->height, p->tile_rows, world, rank);
     a.chunk_samples = std::min<uint32_t>(p->spp, 256u);
     a.chunks_per_pixel = (p->spp + a.chunk_samples - 1) / a.chunk_samples;

@@ -165,7 +165,7 @@ __device__ __forceinline__ double sqrt_seeded(double x)
     y = y * fma(-0.5 * x, y * y, 1.5);
     return x * y;
 }
-template <bool kSeeded> __device__ __forceinline__ float sqrt_sel(float x) { return sqrtf(x); }
+template <bool kSeeded> __device__ __forceinline__ float sqrt_sel(float x) { return kSeeded ? (x > 0.0f ? x * rsqrtf(x) : 0.0f) : sqrtf(x); }   // MUFU.RSQ: 2 ulp
 template <bool kSeeded> __device__ __forceinline__ double sqrt_sel(double x) { return kSeeded ? sqrt_seeded(x) : sqrt(x); }
 
 // inv_a = 1 / |dhat|^2 (dhat is unit only to rounding; hoisted per ray).
@@ -211,23 +211,26 @@ template <typename T> __device__ __forceinline__ T reflectance(T cosine, T ref_i
     return r0 + (T(1) - r0) * (m * m * m * m * m);
 }
 
-template <typename T>
+// kUnit: the caller guarantees that r_dir is already a unit vector and that a Lambertian sample is one too (the
+// renderer's rays and its inversion sampler), so the three unit_vector() calls of the reference are identities up to
+// rounding and are skipped; the unit-level entry points pass kUnit = false and normalise exactly where the reference does.
+template <typename T, bool kUnit = false>
 __device__ __forceinline__ bool scatter(int kind, V3<T> albedo, T param, V3<T> r_dir, V3<T> normal, bool front_face, V3<T> sample,
                                         V3<T>* attenuation, V3<T>* out_dir)
 {
     if (kind == MAT_LAMBERTIAN) {                                                                     // materials.rs:22-30
-        V3<T> d = normal + unit_vector(sample);
+        V3<T> d = normal + (kUnit ? sample : unit_vector(sample));
         if (is_near_zero(d)) d = normal;
         *out_dir = d; *attenuation = albedo;
         return true;
     } else if (kind == MAT_METAL) {                                                                   // materials.rs:50-61
-        V3<T> reflected = unit_vector(reflect(r_dir, normal));
+        V3<T> reflected = kUnit ? reflect(r_dir, normal) : unit_vector(reflect(r_dir, normal));
         V3<T> d = reflected + sample * param;          // drawn even when fuzz == 0 (materials.rs:53)
         *out_dir = d; *attenuation = albedo;
         return !(dot(d, normal) <= T(0));
     } else {                                                                                          // materials.rs:77-104
         T ratio = front_face ? T(1) / param : param;
-        V3<T> ud = unit_vector(r_dir);
+        V3<T> ud = kUnit ? r_dir : unit_vector(r_dir);
         T cos_theta = min_t(T(1), -dot(ud, normal));
         T sin_theta = sqrt_t(T(1) - cos_theta * cos_theta);
         bool can_refract = ratio * sin_theta <= T(1);
@@ -239,9 +242,9 @@ __device__ __forceinline__ bool scatter(int kind, V3<T> albedo, T param, V3<T> r
 }
 
 // miss branch of ray_color (main.rs:54-56)
-template <typename T> __device__ __forceinline__ V3<T> sky(V3<T> dir)
+template <typename T, bool kUnit = false> __device__ __forceinline__ V3<T> sky(V3<T> dir)
 {
-    V3<T> ud = unit_vector(dir);
+    V3<T> ud = kUnit ? dir : unit_vector(dir);
     T t = T(0.5) * (ud.y + T(1));
     return mk<T>(T(1), T(1), T(1)) * (T(1) - t) + mk<T>(T(0.5), T(0.7), T(1.0)) * t;
 }

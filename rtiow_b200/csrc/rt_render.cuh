@@ -18,6 +18,7 @@ template <typename T> struct RenderArgs {
     uint32_t width, height, spp;
     int32_t max_depth;
     T t_min;
+    T inv_wm1, inv_hm1;            // 1/(width-1), 1/(height-1): the jitter denominators of main.rs:131-132
     uint64_t seed;
     // frame partition: this launch renders rows {y : (y / tile_rows) % world == rank}
     uint32_t rank, world, tile_rows, local_rows;
@@ -61,10 +62,14 @@ template <typename T> struct PathState {
     int depth;
 };
 
+// float: one MUFU.RSQ gives 1/|dir| (2 ulp); dhat is then unit to ~2e-7, which the precise test absorbs through inv_a
+__device__ __forceinline__ void inv_and_len(float l2, float* inv, float* len) { *inv = rsqrtf(l2); *len = l2 * *inv; }
+__device__ __forceinline__ void inv_and_len(double l2, double* inv, double* len) { *len = sqrt(l2); *inv = 1.0 / *len; }
+
 template <typename T> __device__ __forceinline__ void start_ray(PathState<T>& ps, V3<T> orig, V3<T> dir, T t_min)
 {
-    const T len = length(dir);
-    ps.o = orig; ps.dhat = dir * (T(1) / len);
+    T inv, len; inv_and_len(length_squared(dir), &inv, &len);
+    ps.o = orig; ps.dhat = dir * inv;
     ps.tmin_n = t_min * len;                        // t is measured in |dir| units (Appendix C.3)
 }
 
@@ -91,7 +96,7 @@ __device__ __forceinline__ bool bounce_step(const SceneDev& sc, const float* soa
     if (!active) return false;
     ++*n_rays;
     if (idx < 0) {                                                            // miss: sky (main.rs:54-56)
-        *radiance = ps.thr * sky(ps.dhat);
+        *radiance = ps.thr * sky<T, sizeof(T) == 4>(ps.dhat);
         return false;
     }
     V3<T> cen; T rad; V3<T> albedo; T param;
@@ -107,12 +112,14 @@ __device__ __forceinline__ bool bounce_step(const SceneDev& sc, const float* soa
     V3<T> n; bool ff; hit_record(p, cen, rad, ps.dhat, &n, &ff);             // sphere.rs:36-39
     ++ps.bounce;
     const Uniform4<T> u = event_uniforms<T>(seed, ps.pix_key, ps.smp, ps.bounce);
-    V3<T> sample;
-    if (kind == MAT_LAMBERTIAN) sample = direct_unit_vector(u.u0, u.u1);      // materials.rs:23
-    else if (kind == MAT_METAL) sample = direct_in_unit_sphere(u.u0, u.u1, u.u2);   // materials.rs:53
-    else sample = mk<T>(u.u0, 0, 0);                                          // materials.rs:96
+    // one unit vector for both diffuse (materials.rs:23) and metal (materials.rs:53: scaled into the ball); xi for glass (materials.rs:96)
+    V3<T> sample = mk<T>(u.u0, 0, 0);
+    if (kind != MAT_DIELECTRIC) {
+        sample = direct_unit_vector(u.u0, u.u1);
+        if (kind == MAT_METAL) sample = sample * cbrt_t(u.u2);
+    }
     V3<T> att, nd;
-    const bool some = scatter(kind, albedo, param, ps.dhat, n, ff, sample, &att, &nd);   // main.rs:47
+    const bool some = scatter<T, sizeof(T) == 4>(kind, albedo, param, ps.dhat, n, ff, sample, &att, &nd);   // main.rs:47
     --ps.depth;
     if (!some || ps.depth <= 0) {                                             // main.rs:51 / main.rs:40-42: black
         *radiance = mk<T>(0, 0, 0);
@@ -121,7 +128,9 @@ __device__ __forceinline__ bool bounce_step(const SceneDev& sc, const float* soa
     ps.thr = ps.thr * att;                                                    // main.rs:49 as a running product
     start_ray(ps, p, nd, t_min);
     ps.self_code = code;
-    ps.self_n = unit_vector(p - cen);
+    const V3<T> pc = p - cen;
+    T inv, len; inv_and_len(length_squared(pc), &inv, &len);
+    ps.self_n = pc * inv;
     return true;
 }
 
@@ -193,8 +202,8 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) render_kernel(const Render
                 const uint32_t j = a.height - 1u - c_y;                 // j = 0 is the bottom row (main.rs:132,141-145)
                 ps.pix_key = j * a.width + c_x;
                 const Uniform4<T> u = event_uniforms<T>(a.seed, ps.pix_key, ps.smp, 0u);
-                const T su = (T(c_x) + u.u0) / T(a.width - 1u);         // main.rs:131
-                const T sv = (T(j) + u.u1) / T(a.height - 1u);          // main.rs:132
+                const T su = (T(c_x) + u.u0) * a.inv_wm1;                // main.rs:131
+                const T sv = (T(j) + u.u1) * a.inv_hm1;                  // main.rs:132
                 T dx, dy; direct_disk(u.u2, u.u3, &dx, &dy);            // camera.rs:48
                 V3<T> ro, rd; get_ray(a.cam, su, sv, dx, dy, &ro, &rd); // main.rs:134
                 start_ray(ps, ro, rd, a.t_min);

@@ -143,14 +143,14 @@ __device__ __forceinline__ void scan_small(const float* __restrict__ s_soa, int 
                 c &= ~(0x80000000u >> k);
                 const int p = (w << 5) + k;
                 if (nc < RT_CAND_CAP) { cand[nc * cand_stride] = (uint16_t)(p - (w0 << 5)); ++nc; }
-                else if (p != self_pos) { const float4 s = small[p]; candidate<float>(o, dhat, inv_a, t_min, mk(s.x, s.y, s.z), s.w, p, &tb, &pb); }
+                else if (p != self_pos) { const float4 s = small[p]; candidate<float, true>(o, dhat, inv_a, t_min, mk(s.x, s.y, s.z), s.w, p, &tb, &pb); }
             }
         }
         const int nmax = __reduce_max_sync(RT_FULL, nc);
         for (int k = 0; k < nmax; ++k) {
             if (k < nc) {
                 const int p = (w0 << 5) + cand[k * cand_stride];
-                if (p != self_pos) { const float4 s = small[p]; candidate<float>(o, dhat, inv_a, t_min, mk(s.x, s.y, s.z), s.w, p, &tb, &pb); }
+                if (p != self_pos) { const float4 s = small[p]; candidate<float, true>(o, dhat, inv_a, t_min, mk(s.x, s.y, s.z), s.w, p, &tb, &pb); }
             }
         }
     }

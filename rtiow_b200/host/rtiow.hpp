@@ -261,7 +261,7 @@ public:
 // ------------------------------------------------------------------------------------------------ the new call
 struct RenderParams {                                     // runtime form of the consts at main.rs:24-28,44,137
     uint32_t width = 200, height = 133; uint32_t spp = 100; int32_t max_depth = 50; double t_min = 0.0001;
-    uint64_t seed = 1; int n_gpus = 1; uint8_t alpha = 255; bool f64 = false; uint32_t tile_rows = 4;
+    uint64_t seed = 1; int n_gpus = 1; uint8_t alpha = 255; bool f64 = false; uint32_t tile_rows = 1;
 };
 
 class RenderError : public std::runtime_error {

@@ -28,11 +28,15 @@ def not_grazing(c, r, o, d, thr=2e-3):
 
 
 def t_err(got_t, ref_t, o, d, c):
-    """error of a root t, relative to max(t, 5 % of the distance to the sphere centre in the same units).
+    """error of a root t, relative to max(t, 10 % of the lengths it is computed from, in the same units).
     t is the difference of two lengths of size ~|o - c| / |d| (sphere.rs:28), so with f32 inputs its absolute error cannot
     be below ~eps32 * |o - c| / |d|; `1e-5 relative` is therefore meant for hits that are not a hair away from the origin."""
     o, d, c = np.asarray(o, float), np.asarray(d, float), np.asarray(c, float)
-    scale = np.maximum(np.abs(ref_t), 0.05 * np.linalg.norm(o - c, axis=-1) / np.linalg.norm(d, axis=-1))
+    # lengths that enter the subtraction: |o - c|, and the coordinates themselves (one f32 ulp of |o| ~ 10 is 1e-6)
+    lengths = np.maximum(np.linalg.norm(o - c, axis=-1), 0.1 * np.linalg.norm(o, axis=-1))
+    # 10 %: an origin a hair inside/outside a surface makes t = tca +- sq a cancellation of two numbers ~|o - c|; ten f32
+    # roundings of that size (6e-8 each) are the floor of ANY f32 evaluation, i.e. ~1e-6 * |o - c| absolute
+    scale = np.maximum(np.abs(ref_t), 0.10 * lengths / np.linalg.norm(d, axis=-1))
     return np.abs(np.asarray(got_t) - np.asarray(ref_t)) / scale
 
 

@@ -18,7 +18,7 @@ te = t_err(got["t"], ref["t"], oo, d, c); te[~m] = 0
 for i in np.argsort(-te)[:6]:
     oc = oo[i] - c[i]; a = d[i] @ d[i]; hb = oc @ d[i]; cc = oc @ oc - r[i] ** 2
     print(f"sphere_hit: te {te[i]:.3g} t_ref {ref['t'][i]:.8g} t_got {got['t'][i]:.8g} |oc| {np.linalg.norm(oc):.4g} r {r[i]:.4g} |d| {np.sqrt(a):.4g} disc/a/r2 {(hb*hb-a*cc)/a/r[i]**2:.4g} tca {-hb/np.sqrt(a):.5g}")
-scene = capi.random_scene(1); sc = o.Scene(**scene); ctx.upload_scene(**scene)
+scene = capi.random_scene(1); scene = {k: (f32(v) if v.dtype == np.float64 else v) for k, v in scene.items()}; sc = o.Scene(**scene); ctx.upload_scene(**scene)
 rng = np.random.default_rng(11)
 ocam = o.camera_new((13, 2, 3), (0, 0, 0), (0, 1, 0), 20.0, 16 / 9, 0.1, 10.0)
 n1 = 60000
