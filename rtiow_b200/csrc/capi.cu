@@ -85,7 +85,20 @@ struct DeviceState {
 struct rtiow_ctx {
     std::vector<DeviceState> dev;
     size_t scene_bytes = 0;
+    std::vector<float4> host_small;      // the culled segment's spheres (cx,cy,cz,r; r = 0 for padding): origin-inside checks
 };
+
+// true if a point (with a safety radius) lies inside or on any sphere of the culled segment: then behind-the-ray culling
+// must be switched off for the call (SceneDev::w_cull = 0), because a ray leaving the INSIDE of a sphere hits it from behind
+static bool origin_inside_culled(const rtiow_ctx* c, double x, double y, double z, double pad)
+{
+    for (const float4& s : c->host_small) {
+        if (s.w == 0.0f) continue;
+        const double dx = x - s.x, dy = y - s.y, dz = z - s.z, r = std::fabs((double)s.w) * (1.0 + 1e-5) + pad;
+        if (dx * dx + dy * dy + dz * dz <= r * r) return true;
+    }
+    return false;
+}
 
 static int init_device(DeviceState& d, int device)
 {
@@ -186,12 +199,31 @@ extern "C" int rtiow_scene_upload(rtiow_ctx* c, const rtiow_spheres* s, const rt
         if (std::fabs(s->radius[i]) > kBigRadius || reach > 4096.0) big_ids.push_back(i); else small_ids.push_back(i);
     }
     const int ns = (int)small_ids.size(), nb = (int)big_ids.size();
-    const int np = (ns + 31) / 32 * 32;
-    if (np > 65536 * 32) return fail(RTIOW_ERR_UNSUPPORTED, "scene too large");
+    // Split the small spheres: those that overlap NO other sphere can contain no ray origin (origins are scatter points on
+    // some sphere's surface, or the camera — checked per render), so the filter may cull them when they lie behind the ray
+    // (filter_word<true>).  Overlapping / nested spheres (hollow glass: r=1 and r=-0.9, BASELINE configs[2]) keep the plain filter.
+    // O(n^2) on the f32-rounded spheres, a few 1e7 pair tests at 10 k spheres.
+    std::vector<char> overlaps(n, 0);
+    {
+        const double tol = 1e-5;
+        for (int i = 0; i < n; ++i)
+            for (int j = i + 1; j < n; ++j) {
+                const double dx = (double)sph[i].x - sph[j].x, dy = (double)sph[i].y - sph[j].y, dz = (double)sph[i].z - sph[j].z;
+                const double rs = std::fabs((double)sph[i].w) + std::fabs((double)sph[j].w) + tol;
+                if (dx * dx + dy * dy + dz * dz < rs * rs) { overlaps[i] = 1; overlaps[j] = 1; }
+            }
+    }
+    std::vector<int> order; order.reserve(ns + 64);
+    for (int id : small_ids) if (!overlaps[id]) order.push_back(id);
+    const int np_cull = (int)order.size() / 32 * 32;       // whole words only; the mixed word is filtered without culling
+    for (int id : small_ids) if (overlaps[id]) order.push_back(id);
+    while (order.size() % 32) order.push_back(-1);
+    const int np = (int)order.size();
+    if (np > 65535 * 32) return fail(RTIOW_ERR_UNSUPPORTED, "scene too large");
     std::vector<float> soa((size_t)4 * np); std::vector<float4> small(np); std::vector<int> small_idx(np);
     for (int p = 0; p < np; ++p) {
-        if (p < ns) {
-            const float4 v = sph[small_ids[p]];
+        if (order[p] >= 0) {
+            const float4 v = sph[order[p]];
             soa[p] = v.x; soa[np + p] = v.y; soa[2 * (size_t)np + p] = v.z;
             // K = |c|^2 - r^2 of the f32 sphere, in f64, lowered by the filter slack (RT_FILTER_SLACK, rt_scene.cuh)
             // and rounded toward -inf: the filter may only err towards keeping a sphere
@@ -199,12 +231,13 @@ extern "C" int rtiow_scene_upload(rtiow_ctx* c, const rtiow_spheres* s, const rt
             const double K = c2 - r2 - (double)RT_FILTER_SLACK * (c2 + r2) - 1e-30;
             float Kf = (float)K; if ((double)Kf > K) Kf = std::nextafterf(Kf, -INFINITY);
             soa[3 * (size_t)np + p] = Kf;
-            small[p] = v; small_idx[p] = small_ids[p];
+            small[p] = v; small_idx[p] = order[p];
         } else {       // padding: C = 1e30 can never be reached by hb^2
             soa[p] = 0; soa[np + p] = 0; soa[2 * (size_t)np + p] = 0; soa[3 * (size_t)np + p] = 1e30f;
             small[p] = make_float4(0, 0, 0, 0); small_idx[p] = -1;
         }
     }
+    c->host_small.assign(small.begin(), small.begin() + np_cull);
     std::vector<double4> big(nb); for (int b = 0; b < nb; ++b) big[b] = sphd[big_ids[b]];
     c->scene_bytes = 0;
     for (auto& d : c->dev) {
@@ -218,7 +251,7 @@ extern "C" int rtiow_scene_upload(rtiow_ctx* c, const rtiow_spheres* s, const rt
         UP(d.sph, sph, n, float4); UP(d.sphd, sphd, n, double4); UP(d.mat, mat, n, float4); UP(d.matd, matd, n, double4); UP(d.kind, kind, n, uint8_t);
 #undef UP
         CU(cudaStreamSynchronize(d.stream));
-        d.scene.soa = d.soa.p; d.scene.small = d.small.p; d.scene.small_idx = d.small_idx.p; d.scene.np = np;
+        d.scene.soa = d.soa.p; d.scene.small = d.small.p; d.scene.small_idx = d.small_idx.p; d.scene.np = np; d.scene.w_cull = np_cull / 32;
         d.scene.big = d.big.p; d.scene.big_idx = d.big_idx.p; d.scene.nb = nb;
         d.scene.sph = d.sph.p; d.scene.sphd = d.sphd.p; d.scene.mat = d.mat.p; d.scene.matd = d.matd.p; d.scene.kind = d.kind.p; d.scene.n = n;
         d.has_scene = true;
@@ -342,10 +375,11 @@ template <typename K> static int prep_kernel(K kernel, size_t smem, int threads,
 
 template <typename T>
 static int launch_render(DeviceState& d, const rtiow_camera* cam, const rtiow_params* p, uint32_t rank, uint32_t world, uint32_t* d_tiles,
-                         cudaStream_t st, uint32_t* launches)
+                         cudaStream_t st, uint32_t* launches, bool cull_ok)
 {
     RenderArgs<T> a;
     a.scene = d.scene; a.cam = to_dev_camera<T>(*cam);
+    if (!cull_ok) a.scene.w_cull = 0;                 // the camera lens touches a sphere of the culled segment
     a.width = p->width; a.height = p->height; a.spp = p->spp; a.max_depth = p->max_depth; a.t_min = (T)p->t_min; a.seed = p->seed;
     a.inv_wm1 = (T)(1.0 / (double)(p->width - 1)); a.inv_hm1 = (T)(1.0 / (double)(p->height - 1));
     a.rank = rank; a.world = world; a.tile_rows = p->tile_rows; a.local_rows = rows_of_rank(p->height, p->tile_rows, world, rank);
@@ -397,13 +431,14 @@ static int launch_render(DeviceState& d, const rtiow_camera* cam, const rtiow_pa
     return RTIOW_OK;
 }
 
-static int render_tiles(DeviceState& d, const rtiow_camera* cam, const rtiow_params* p, uint32_t rank, uint32_t world, uint32_t* d_tiles,
+static int render_tiles(const rtiow_ctx* c, DeviceState& d, const rtiow_camera* cam, const rtiow_params* p, uint32_t rank, uint32_t world, uint32_t* d_tiles,
                         cudaStream_t st, uint32_t* launches)
 {
+    const bool cull_ok = !origin_inside_culled(c, cam->origin[0], cam->origin[1], cam->origin[2], std::fabs(cam->lens_radius) * 1.001 + 1e-6);
     if (!d.has_scene) return fail(RTIOW_ERR_INVALID_ARG, "no scene uploaded (call rtiow_scene_upload first)");
     CU(cudaSetDevice(d.device));
-    return p->precision == RTIOW_PRECISION_F64 ? launch_render<double>(d, cam, p, rank, world, d_tiles, st, launches)
-                                               : launch_render<float>(d, cam, p, rank, world, d_tiles, st, launches);
+    return p->precision == RTIOW_PRECISION_F64 ? launch_render<double>(d, cam, p, rank, world, d_tiles, st, launches, cull_ok)
+                                               : launch_render<float>(d, cam, p, rank, world, d_tiles, st, launches, cull_ok);
 }
 
 static double now_ms()
@@ -423,7 +458,7 @@ extern "C" int rtiow_render_tiles_device(rtiow_ctx* c, const rtiow_camera* cam, 
     const double t0 = now_ms();
     uint32_t launches = 0;
     if (stats) CU(cudaEventRecord(d.ev0, st));
-    rc = render_tiles(d, cam, p, (uint32_t)rank, (uint32_t)world, (uint32_t*)d_tiles, st, &launches); if (rc) return rc;
+    rc = render_tiles(c, d, cam, p, (uint32_t)rank, (uint32_t)world, (uint32_t*)d_tiles, st, &launches); if (rc) return rc;
     if (stats) {
         CU(cudaEventRecord(d.ev1, st));
         CU(cudaMemcpyAsync(d.pinned_cnt, d.counters.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -474,7 +509,7 @@ extern "C" int rtiow_render(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_p
     if (world == 1) {
         CU(d0.tiles.resize(tile_px));
         CU(cudaEventRecord(d0.ev0, d0.stream));
-        rc = render_tiles(d0, cam, p, 0, 1, d0.tiles.p, d0.stream, &launches); if (rc) return rc;
+        rc = render_tiles(c, d0, cam, p, 0, 1, d0.tiles.p, d0.stream, &launches); if (rc) return rc;
         CU(cudaEventRecord(d0.ev1, d0.stream));
         d_final = d0.tiles.p;                                  // world == 1: rank-local order IS top-down
     } else {
@@ -486,7 +521,7 @@ extern "C" int rtiow_render(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_p
             uint32_t* dst = nullptr;
             if (r == 0) dst = d0.gathered.p; else { CU(d.tiles.resize(tile_px)); dst = d.tiles.p; }
             if (r == 0) CU(cudaEventRecord(d.ev0, d.stream));
-            rc = render_tiles(d, cam, p, r, world, dst, d.stream, &launches); if (rc) return rc;
+            rc = render_tiles(c, d, cam, p, r, world, dst, d.stream, &launches); if (rc) return rc;
             if (r == 0) CU(cudaEventRecord(d.ev1, d.stream));
             if (r != 0) {
                 const size_t bytes = (size_t)rows_of_rank(p->height, p->tile_rows, world, r) * p->width * 4;
@@ -584,21 +619,23 @@ extern "C" int rtiow_hitlist_batch(rtiow_ctx* c, int precision, int64_t n, const
     BATCH_PROLOGUE();
     if (!d.has_scene) return fail(RTIOW_ERR_INVALID_ARG, "no scene uploaded");
     if (n == 0) return RTIOW_OK;
+    SceneDev scene = d.scene;
+    for (int64_t i = 0; i < n && scene.w_cull; ++i) if (origin_inside_culled(c, orig[3 * i], orig[3 * i + 1], orig[3 * i + 2], 1e-6)) scene.w_cull = 0;
     double *dor, *dd, *dt, *dp, *dn; int32_t *dh, *di, *dff;
     CU(S.in(orig, N3, &dor)); CU(S.in(dir, N3, &dd));
     CU(S.out(n, &dh)); CU(S.out(n, &di)); CU(S.out(n, &dt)); CU(S.out(N3, &dp)); CU(S.out(N3, &dn)); CU(S.out(n, &dff));
     if (precision == RTIOW_PRECISION_F64) {
-        hitlist_kernel<double, false, 256><<<grid, 256, 0, d.stream>>>(d.scene, n, dor, dd, t_min, dh, di, dt, dp, dn, dff);
+        hitlist_kernel<double, false, 256><<<grid, 256, 0, d.stream>>>(scene, n, dor, dd, t_min, dh, di, dt, dp, dn, dff);
     } else {
         const ScanCfg cfg = pick_cfg(d.scene.np);
         if (cfg.variant == 0) {
-            hitlist_kernel<float, true, 256><<<grid, 256, cfg.smem, d.stream>>>(d.scene, n, dor, dd, t_min, dh, di, dt, dp, dn, dff);
+            hitlist_kernel<float, true, 256><<<grid, 256, cfg.smem, d.stream>>>(scene, n, dor, dd, t_min, dh, di, dt, dp, dn, dff);
         } else if (cfg.variant == 1) {
             auto k = hitlist_kernel<float, true, 512>;
             CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
-            k<<<(unsigned)((n + 511) / 512), 512, cfg.smem, d.stream>>>(d.scene, n, dor, dd, t_min, dh, di, dt, dp, dn, dff);
+            k<<<(unsigned)((n + 511) / 512), 512, cfg.smem, d.stream>>>(scene, n, dor, dd, t_min, dh, di, dt, dp, dn, dff);
         } else {
-            hitlist_kernel<float, false, 256><<<grid, 256, cfg.smem, d.stream>>>(d.scene, n, dor, dd, t_min, dh, di, dt, dp, dn, dff);
+            hitlist_kernel<float, false, 256><<<grid, 256, cfg.smem, d.stream>>>(scene, n, dor, dd, t_min, dh, di, dt, dp, dn, dff);
         }
     }
     CU(cudaGetLastError());
@@ -691,21 +728,23 @@ extern "C" int rtiow_ray_color_batch(rtiow_ctx* c, int precision, int64_t n, con
     BATCH_PROLOGUE();
     if (!d.has_scene) return fail(RTIOW_ERR_INVALID_ARG, "no scene uploaded");
     if (n == 0) return RTIOW_OK;
+    SceneDev scene = d.scene;
+    for (int64_t i = 0; i < n && scene.w_cull; ++i) if (origin_inside_culled(c, orig[3 * i], orig[3 * i + 1], orig[3 * i + 2], 1e-6)) scene.w_cull = 0;
     double *dor, *dd, *dcol; uint32_t *dpx, *dsm; unsigned long long* dr;
     CU(S.in(orig, N3, &dor)); CU(S.in(dir, N3, &dd)); CU(S.in(pixel, n, &dpx)); CU(S.in(sample, n, &dsm));
     CU(S.out(N3, &dcol)); CU(S.out(n, &dr));
     if (precision == RTIOW_PRECISION_F64) {
-        ray_color_kernel<double, false, 256><<<grid, 256, 0, d.stream>>>(d.scene, n, dor, dd, dpx, dsm, seed, max_depth, t_min, dcol, dr);
+        ray_color_kernel<double, false, 256><<<grid, 256, 0, d.stream>>>(scene, n, dor, dd, dpx, dsm, seed, max_depth, t_min, dcol, dr);
     } else {
         const ScanCfg cfg = pick_cfg(d.scene.np);
         if (cfg.variant == 0) {
-            ray_color_kernel<float, true, 256><<<grid, 256, cfg.smem, d.stream>>>(d.scene, n, dor, dd, dpx, dsm, seed, max_depth, t_min, dcol, dr);
+            ray_color_kernel<float, true, 256><<<grid, 256, cfg.smem, d.stream>>>(scene, n, dor, dd, dpx, dsm, seed, max_depth, t_min, dcol, dr);
         } else if (cfg.variant == 1) {
             auto k = ray_color_kernel<float, true, 512>;
             CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
-            k<<<(unsigned)((n + 511) / 512), 512, cfg.smem, d.stream>>>(d.scene, n, dor, dd, dpx, dsm, seed, max_depth, t_min, dcol, dr);
+            k<<<(unsigned)((n + 511) / 512), 512, cfg.smem, d.stream>>>(scene, n, dor, dd, dpx, dsm, seed, max_depth, t_min, dcol, dr);
         } else {
-            ray_color_kernel<float, false, 256><<<grid, 256, cfg.smem, d.stream>>>(d.scene, n, dor, dd, dpx, dsm, seed, max_depth, t_min, dcol, dr);
+            ray_color_kernel<float, false, 256><<<grid, 256, cfg.smem, d.stream>>>(scene, n, dor, dd, dpx, dsm, seed, max_depth, t_min, dcol, dr);
         }
     }
     CU(cudaGetLastError());

@@ -22,6 +22,7 @@ struct SceneDev {
     const float4* small;
     const int* small_idx;
     int np;
+    int w_cull;             // 32-sphere words [0, w_cull) may use behind-the-ray culling (rt_scene.cuh, filter_word)
     const double4* big;
     const int* big_idx;
     int nb;
@@ -88,8 +89,57 @@ __device__ __forceinline__ void candidate_self(V3<T> dhat, T inv_a, T t_min, V3<
 //   candidates (a few per ray): positions appended to a per-lane list in shared memory, then the
 //     whole warp drains its lists in lock-step through candidate<float>.
 // s_soa: [4][np] floats in shared memory (or global when the scene does not fit).
+// Per-ray constants of the filter (rt_scene.cuh header comment): broadcast scalars for the packed ops.
+struct FilterRay {
+    float2 M2OX, M2OY, M2OZ, DX, DY, DZ, NOD, OO;
+};
+__device__ __forceinline__ FilterRay make_filter_ray(V3<float> o, V3<float> dhat)
+{
+    FilterRay f;
+    const float oo = length_squared(o);
+    f.M2OX = bc2(-2.0f * o.x); f.M2OY = bc2(-2.0f * o.y); f.M2OZ = bc2(-2.0f * o.z);
+    f.DX = bc2(dhat.x); f.DY = bc2(dhat.y); f.DZ = bc2(dhat.z);
+    f.NOD = bc2(-dot(o, dhat));
+    f.OO = bc2(oo - RT_FILTER_SLACK * oo);
+    return f;
+}
+
+// One 32-sphere word of the filter.  kCull: the last op is hb*|hb| - C instead of hb*hb - C (the |.| is an operand
+// modifier of FFMA2, so it is free): a sphere whose centre lies BEHIND the ray (hb < 0) then only passes if the origin
+// is deep inside it, i.e. spheres entirely behind an outside origin — about half of all line/sphere intersections of a
+// bounce ray — never become candidates.  Valid only for spheres no ray origin can be inside of (see `n_cull` below).
+template <bool kCull>
+__device__ __forceinline__ unsigned filter_word(const float4* __restrict__ CX, const float4* __restrict__ CY, const float4* __restrict__ CZ,
+                                                const float4* __restrict__ KK, int q0, int q_next_word, const FilterRay& f,
+                                                float4& ncx, float4& ncy, float4& ncz, float4& nkk)
+{
+    unsigned m = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const float4 cx = ncx, cy = ncy, cz = ncz, kk = nkk;
+        const int qn = q < 7 ? q0 + q + 1 : q_next_word;
+        ncx = CX[qn]; ncy = CY[qn]; ncz = CZ[qn]; nkk = KK[qn];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float2 X = h ? make_float2(cx.z, cx.w) : make_float2(cx.x, cx.y);
+            const float2 Y = h ? make_float2(cy.z, cy.w) : make_float2(cy.x, cy.y);
+            const float2 Z = h ? make_float2(cz.z, cz.w) : make_float2(cz.x, cz.y);
+            const float2 K = h ? make_float2(kk.z, kk.w) : make_float2(kk.x, kk.y);
+            const float2 hb = ffma2(X, f.DX, ffma2(Y, f.DY, ffma2(Z, f.DZ, f.NOD)));
+            const float2 C = ffma2(X, f.M2OX, ffma2(Y, f.M2OY, ffma2(Z, f.M2OZ, fadd2(K, f.OO))));
+            const float2 hb2 = kCull ? make_float2(fabsf(hb.x), fabsf(hb.y)) : hb;
+            const float2 disc = ffma2(hb, hb2, neg2(C));
+            m = __funnelshift_l(__float_as_uint(disc.x), m, 1);
+            m = __funnelshift_l(__float_as_uint(disc.y), m, 1);
+        }
+    }
+    return m;
+}
+
+// words [0, w_cull) hold spheres that provably contain no ray origin (they overlap no other sphere and not the
+// camera lens): filtered with behind-the-ray culling; words [w_cull, n_words) hold the rest, filtered without.
 template <bool kSmem>
-__device__ __forceinline__ void scan_small(const float* __restrict__ s_soa, int np, const float4* __restrict__ small,
+__device__ __forceinline__ void scan_small(const float* __restrict__ s_soa, int np, int w_cull, const float4* __restrict__ small,
                                            V3<float> o, V3<float> dhat, float inv_a, float t_min, int self_pos, V3<float> self_n,
                                            uint16_t* cand, int cand_stride, float* t_best, int* p_best)
 {
@@ -98,11 +148,7 @@ __device__ __forceinline__ void scan_small(const float* __restrict__ s_soa, int 
     const float4* CY = CX + n4;
     const float4* CZ = CY + n4;
     const float4* KK = CZ + n4;
-    const float oo = length_squared(o);
-    const float2 M2OX = bc2(-2.0f * o.x), M2OY = bc2(-2.0f * o.y), M2OZ = bc2(-2.0f * o.z);
-    const float2 DX = bc2(dhat.x), DY = bc2(dhat.y), DZ = bc2(dhat.z);
-    const float2 NOD = bc2(-dot(o, dhat));
-    const float2 OO = bc2(oo - RT_FILTER_SLACK * oo);
+    const FilterRay f = make_filter_ray(o, dhat);
     const int n_words = np >> 5;
     int pb = *p_best; float tb = *t_best;
     // the sphere the ray starts on is tested on its own, independently of the filter
@@ -116,27 +162,10 @@ __device__ __forceinline__ void scan_small(const float* __restrict__ s_soa, int 
         const int w1 = min(w0 + RT_SEG_WORDS, n_words);
         int nc = 0;
         for (int w = w0; w < w1; ++w) {
-            unsigned m = 0;
             const int q0 = w << 3;
             const int q_next_word = (w + 1 < n_words) ? q0 + 8 : q0;     // the last word re-reads its first quad (unused)
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const float4 cx = ncx, cy = ncy, cz = ncz, kk = nkk;
-                const int qn = q < 7 ? q0 + q + 1 : q_next_word;
-                ncx = CX[qn]; ncy = CY[qn]; ncz = CZ[qn]; nkk = KK[qn];
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const float2 X = h ? make_float2(cx.z, cx.w) : make_float2(cx.x, cx.y);
-                    const float2 Y = h ? make_float2(cy.z, cy.w) : make_float2(cy.x, cy.y);
-                    const float2 Z = h ? make_float2(cz.z, cz.w) : make_float2(cz.x, cz.y);
-                    const float2 K = h ? make_float2(kk.z, kk.w) : make_float2(kk.x, kk.y);
-                    const float2 hb = ffma2(X, DX, ffma2(Y, DY, ffma2(Z, DZ, NOD)));
-                    const float2 C = ffma2(X, M2OX, ffma2(Y, M2OY, ffma2(Z, M2OZ, fadd2(K, OO))));
-                    const float2 disc = ffma2(hb, hb, neg2(C));
-                    m = __funnelshift_l(__float_as_uint(disc.x), m, 1);
-                    m = __funnelshift_l(__float_as_uint(disc.y), m, 1);
-                }
-            }
+            const unsigned m = w < w_cull ? filter_word<true>(CX, CY, CZ, KK, q0, q_next_word, f, ncx, ncy, ncz, nkk)
+                                          : filter_word<false>(CX, CY, CZ, KK, q0, q_next_word, f, ncx, ncy, ncz, nkk);
             unsigned c = ~m;                         // bit (31-k) set: sphere 32w+k passed the filter
             while (c) {
                 const int k = __clz(c);
@@ -168,7 +197,7 @@ __device__ __forceinline__ HitF closest_hit(const SceneDev& sc, const float* s_s
     const float inv_a = 1.0f / length_squared(dhat);
     float tb = __int_as_float(0x7f800000);   // f64::INFINITY at main.rs:44
     int pb = -1;
-    scan_small<kSmem>(s_soa, sc.np, sc.small, o, dhat, inv_a, t_min, self_code, self_n, cand, cand_stride, &tb, &pb);
+    scan_small<kSmem>(s_soa, sc.np, sc.w_cull, sc.small, o, dhat, inv_a, t_min, self_code, self_n, cand, cand_stride, &tb, &pb);
     HitF h; h.t = tb; h.idx = pb >= 0 ? sc.small_idx[pb] : -1; h.code = pb;
     if (sc.nb > 0) {
         const V3<double> od = mk<double>(o.x, o.y, o.z), dd = mk<double>(dhat.x, dhat.y, dhat.z);
