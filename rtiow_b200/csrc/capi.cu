@@ -85,6 +85,7 @@ struct DeviceState {
 struct rtiow_ctx {
     std::vector<DeviceState> dev;
     size_t scene_bytes = 0;
+    bool peer_ok = true;                 // every device can store into device 0's memory (NVLink P2P): fused epilogue + gather
     std::vector<float4> host_small;      // the culled segment's spheres (cx,cy,cz,r; r = 0 for padding): origin-inside checks
 };
 
@@ -131,7 +132,14 @@ static int create_ctx(const std::vector<int>& devices, rtiow_ctx** out)
     for (size_t i = 1; i < devices.size(); ++i) {
         int can = 0;
         cudaDeviceCanAccessPeer(&can, devices[i], devices[0]);
-        if (can) { cudaSetDevice(devices[i]); cudaError_t e = cudaDeviceEnablePeerAccess(devices[0], 0); if (e != cudaSuccess) cudaGetLastError(); }
+        bool ok = false;
+        if (can) {
+            cudaSetDevice(devices[i]);
+            cudaError_t e = cudaDeviceEnablePeerAccess(devices[0], 0);
+            ok = (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled);
+            if (e != cudaSuccess) cudaGetLastError();
+        }
+        if (!ok) c->peer_ok = false;
     }
     *out = c;
     return RTIOW_OK;
@@ -375,7 +383,7 @@ template <typename K> static int prep_kernel(K kernel, size_t smem, int threads,
 
 template <typename T>
 static int launch_render(DeviceState& d, const rtiow_camera* cam, const rtiow_params* p, uint32_t rank, uint32_t world, uint32_t* d_tiles,
-                         cudaStream_t st, uint32_t* launches, bool cull_ok)
+                         cudaStream_t st, uint32_t* launches, bool cull_ok, uint32_t* peer_frame)
 {
     RenderArgs<T> a;
     a.scene = d.scene; a.cam = to_dev_camera<T>(*cam);
@@ -425,20 +433,23 @@ static int launch_render(DeviceState& d, const rtiow_camera* cam, const rtiow_pa
         }
     }
     CU(cudaGetLastError());
-    finalize_kernel<<<(unsigned)((n_lp + 255) / 256), 256, 0, st>>>(d.accum.p, (uint32_t)n_lp, p->spp, p->alpha, d_tiles);
+    if (peer_frame)      // fused quantise + gather: stores go to rank 0's frame through peer memory
+        finalize_to_frame_kernel<<<(unsigned)((n_lp + 255) / 256), 256, 0, st>>>(d.accum.p, (uint32_t)n_lp, p->spp, p->alpha, p->width, p->tile_rows, world, rank, peer_frame);
+    else
+        finalize_kernel<<<(unsigned)((n_lp + 255) / 256), 256, 0, st>>>(d.accum.p, (uint32_t)n_lp, p->spp, p->alpha, d_tiles);
     CU(cudaGetLastError());
     *launches += 2;
     return RTIOW_OK;
 }
 
 static int render_tiles(const rtiow_ctx* c, DeviceState& d, const rtiow_camera* cam, const rtiow_params* p, uint32_t rank, uint32_t world, uint32_t* d_tiles,
-                        cudaStream_t st, uint32_t* launches)
+                        cudaStream_t st, uint32_t* launches, uint32_t* peer_frame = nullptr)
 {
     const bool cull_ok = !origin_inside_culled(c, cam->origin[0], cam->origin[1], cam->origin[2], std::fabs(cam->lens_radius) * 1.001 + 1e-6);
     if (!d.has_scene) return fail(RTIOW_ERR_INVALID_ARG, "no scene uploaded (call rtiow_scene_upload first)");
     CU(cudaSetDevice(d.device));
-    return p->precision == RTIOW_PRECISION_F64 ? launch_render<double>(d, cam, p, rank, world, d_tiles, st, launches, cull_ok)
-                                               : launch_render<float>(d, cam, p, rank, world, d_tiles, st, launches, cull_ok);
+    return p->precision == RTIOW_PRECISION_F64 ? launch_render<double>(d, cam, p, rank, world, d_tiles, st, launches, cull_ok, peer_frame)
+                                               : launch_render<float>(d, cam, p, rank, world, d_tiles, st, launches, cull_ok, peer_frame);
 }
 
 static double now_ms()
@@ -513,28 +524,35 @@ extern "C" int rtiow_render(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_p
         CU(cudaEventRecord(d0.ev1, d0.stream));
         d_final = d0.tiles.p;                                  // world == 1: rank-local order IS top-down
     } else {
-        // interleaved row tiles on every GPU, gathered into device 0 over NVLink peer copies
-        CU(d0.gathered.resize(tile_px * world)); CU(d0.frame.resize((size_t)p->width * p->height));
+        // interleaved row tiles on every GPU.  With NVLink peer access (every B200 box) each rank's epilogue stores its
+        // pixels straight into device 0's top-down frame (finalize_to_frame_kernel): compute and gather are one kernel,
+        // nothing is staged.  Without peer access: tile buffers + cudaMemcpyPeerAsync + de-interleave.
+        CU(d0.frame.resize((size_t)p->width * p->height));
+        if (!c->peer_ok) CU(d0.gathered.resize(tile_px * world));
         for (uint32_t r = 0; r < world; ++r) {
             DeviceState& d = c->dev[r];
             CU(cudaSetDevice(d.device));
             uint32_t* dst = nullptr;
-            if (r == 0) dst = d0.gathered.p; else { CU(d.tiles.resize(tile_px)); dst = d.tiles.p; }
+            if (!c->peer_ok) { if (r == 0) dst = d0.gathered.p; else { CU(d.tiles.resize(tile_px)); dst = d.tiles.p; } }
             if (r == 0) CU(cudaEventRecord(d.ev0, d.stream));
-            rc = render_tiles(c, d, cam, p, r, world, dst, d.stream, &launches); if (rc) return rc;
+            rc = render_tiles(c, d, cam, p, r, world, dst, d.stream, &launches, c->peer_ok ? d0.frame.p : nullptr); if (rc) return rc;
             if (r == 0) CU(cudaEventRecord(d.ev1, d.stream));
             if (r != 0) {
-                const size_t bytes = (size_t)rows_of_rank(p->height, p->tile_rows, world, r) * p->width * 4;
-                CU(cudaMemcpyPeerAsync(d0.gathered.p + tile_px * r, d0.device, d.tiles.p, d.device, bytes, d.stream));
+                if (!c->peer_ok) {
+                    const size_t bytes = (size_t)rows_of_rank(p->height, p->tile_rows, world, r) * p->width * 4;
+                    CU(cudaMemcpyPeerAsync(d0.gathered.p + tile_px * r, d0.device, d.tiles.p, d.device, bytes, d.stream));
+                }
                 CU(cudaEventRecord(d.ev_done, d.stream));
             }
         }
         CU(cudaSetDevice(d0.device));
         for (uint32_t r = 1; r < world; ++r) CU(cudaStreamWaitEvent(d0.stream, c->dev[r].ev_done, 0));
-        const size_t npx = (size_t)p->width * p->height;
-        deinterleave_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, d0.stream>>>(d0.gathered.p, p->width, p->height, p->tile_rows, world, tile_px, d0.frame.p);
-        CU(cudaGetLastError());
-        ++launches;
+        if (!c->peer_ok) {
+            const size_t npx = (size_t)p->width * p->height;
+            deinterleave_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, d0.stream>>>(d0.gathered.p, p->width, p->height, p->tile_rows, world, tile_px, d0.frame.p);
+            CU(cudaGetLastError());
+            ++launches;
+        }
         d_final = d0.frame.p;
     }
     CU(cudaMemcpyAsync(d0.pinned, d_final, frame_bytes, cudaMemcpyDeviceToHost, d0.stream));

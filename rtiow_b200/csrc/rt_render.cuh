@@ -243,6 +243,22 @@ __global__ void finalize_kernel(const unsigned long long* __restrict__ accum, ui
     out_rgba[i] = to_rgba<double>(sum, alpha, (uint64_t)spp);
 }
 
+// The same epilogue FUSED with the gather (single-process multi-GPU): each rank's quantised pixel is stored straight
+// into its top-down place in rank 0's frame.  `frame` is a peer pointer (cudaDeviceEnablePeerAccess), so for ranks > 0
+// these are st.global over NVLink — no tile buffer, no copy, no de-interleave pass.  Rows are written as whole
+// 4-byte-per-pixel runs, i.e. coalesced 128-byte stores.
+__global__ void finalize_to_frame_kernel(const unsigned long long* __restrict__ accum, uint32_t n_lp, uint32_t spp, uint32_t alpha,
+                                         uint32_t width, uint32_t tile_rows, uint32_t world, uint32_t rank, uint32_t* __restrict__ frame)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_lp) return;
+    const double k = 1.0 / 4294967296.0;
+    const V3<double> sum = mk<double>((double)accum[i] * k, (double)accum[n_lp + i] * k, (double)accum[2 * (size_t)n_lp + i] * k);
+    const uint32_t lr = i / width, x = i - lr * width;
+    const uint32_t y = local_to_global_row(lr, tile_rows, world, rank);
+    frame[(size_t)y * width + x] = to_rgba<double>(sum, alpha, (uint64_t)spp);
+}
+
 // gathered tile buffers (rank-major, rank-local rows) -> top-down frame
 __global__ void deinterleave_kernel(const uint32_t* __restrict__ gathered, uint32_t width, uint32_t height, uint32_t tile_rows,
                                     uint32_t world, size_t tile_buf_pixels, uint32_t* __restrict__ frame)
