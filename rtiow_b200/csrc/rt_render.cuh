@@ -5,8 +5,8 @@
 // one PATH at a time; when its path ends (miss -> sky, absorbed, depth exhausted) the lane pulls the
 // next (pixel, sample) from its warp's chunk, so the sphere scan — >95 % of the work — always runs
 // with 32 live lanes regardless of the heavy-tailed path length (1..max_depth rays).
-// Sample radiance is accumulated in 32.32 fixed point (integer adds are associative), so the
-// image is bit-identical for any chunk size, grid size or GPU count.
+// Sample radiance is accumulated in 32.32 fixed point with RED.ADD.U64 (integer adds are associative),
+// so the image is bit-identical for any chunk size, grid size or GPU count.
 #pragma once
 #include "rt_scene.cuh"
 
@@ -158,8 +158,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) render_kernel(const Render
     PathState<T> ps;
     ps.o = mk<T>(0, 0, 0); ps.dhat = mk<T>(0, 1, 0); ps.thr = mk<T>(0, 0, 0); ps.self_n = mk<T>(0, 1, 0);
     ps.tmin_n = T(0); ps.self_code = RT_SELF_NONE; ps.pix_key = 0; ps.smp = 0; ps.bounce = 0; ps.depth = 0;
-    uint32_t acc_lp = 0xffffffffu;                      // local pixel the accumulators belong to
-    unsigned long long acc_r = 0, acc_g = 0, acc_b = 0;
+    uint32_t acc_lp = 0;                                // local pixel of the path in flight
     uint32_t n_rays = 0;
     // ---- warp-uniform work cursor ---------------------------------------------------------------
     uint32_t cs = 0, ce = 0, c_lp = 0, c_x = 0, c_y = 0;
@@ -190,14 +189,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) render_kernel(const Render
             const uint32_t avail = ce - cs;
             const uint32_t r = __popc(need & lt_mask);
             if (!active && r < avail) {
-                if (acc_lp != c_lp) {                   // flush the previous pixel's partial sums
-                    if (acc_lp != 0xffffffffu) {
-                        atomicAdd(a.accum + acc_lp, acc_r);
-                        atomicAdd(a.accum + n_lp_stride + acc_lp, acc_g);
-                        atomicAdd(a.accum + 2 * (size_t)n_lp_stride + acc_lp, acc_b);
-                    }
-                    acc_lp = c_lp; acc_r = acc_g = acc_b = 0;
-                }
+                acc_lp = c_lp;
                 ps.smp = cs + r;
                 const uint32_t j = a.height - 1u - c_y;                 // j = 0 is the bottom row (main.rs:132,141-145)
                 ps.pix_key = j * a.width + c_x;
@@ -219,12 +211,13 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) render_kernel(const Render
         V3<T> rad = mk<T>(0, 0, 0);
         const bool was = active;
         active = bounce_step<T, kSmem>(a.scene, soa, cand, kThreads, a.seed, a.t_min, active, ps, &rad, &n_rays);
-        if (was && !active) { acc_r += to_fix(rad.x); acc_g += to_fix(rad.y); acc_b += to_fix(rad.z); }   // pixel_color += ray_color (main.rs:135)
-    }
-    if (acc_lp != 0xffffffffu) {
-        atomicAdd(a.accum + acc_lp, acc_r);
-        atomicAdd(a.accum + n_lp_stride + acc_lp, acc_g);
-        atomicAdd(a.accum + 2 * (size_t)n_lp_stride + acc_lp, acc_b);
+        // pixel_color += ray_color (main.rs:135): 32.32 fixed-point RED.ADD.U64 straight into the frame's accumulators
+        // (integer adds commute: any order, any GPU count, same bits); black paths add nothing
+        if (was && !active && (rad.x != T(0) || rad.y != T(0) || rad.z != T(0))) {
+            atomicAdd(a.accum + acc_lp, to_fix(rad.x));
+            atomicAdd(a.accum + n_lp_stride + acc_lp, to_fix(rad.y));
+            atomicAdd(a.accum + 2 * (size_t)n_lp_stride + acc_lp, to_fix(rad.z));
+        }
     }
     // rays traced by this warp -> one atomic (world.hit call count, main.rs:44)
     uint32_t wr = __reduce_add_sync(RT_FULL, n_rays);

@@ -50,8 +50,10 @@ def test_cfg4_ten_thousand_spheres_full_size(ctx, capi, oracle, scene_factory):
     assert ok, f"only {f:.4%} of the band within 1 LSB of the oracle"
     sky, _, _ = oracle.render(sc, final_camera(oracle, W / H), W, H, 4, seed=1, rows=(0, 2))
     assert np.abs(img[:2, :, :3].astype(int) - sky[:2, :, :3].astype(int)).max() <= 1           # sky rows do not depend on spp beyond 1 LSB
-    # the 256-spp frame is the converged version of the 4-spp one
-    assert abs(img[..., :3].astype(float).mean() - img4[..., :3].astype(float).mean()) < 1.0
+    # the 256-spp frame is the converged version of the 4-spp one: equal means in LINEAR radiance (the sqrt of to_rgba makes
+    # the 8-bit mean of a noisy frame ~1 LSB darker, Jensen)
+    lin = lambda im: ((im[..., :3].astype(float) + 0.5) / 256.0) ** 2
+    assert abs(lin(img).mean() - lin(img4).mean()) < 4e-3
 
 
 def test_cfg5_4k_1024spp_full_size(ctx_final, capi, oracle, final_scene):

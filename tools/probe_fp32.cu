@@ -459,6 +459,41 @@ __global__ void __launch_bounds__(256) k_scan8_const(float* out, int n, int iter
   }
   out[blockIdx.x*blockDim.x+threadIdx.x]=acc;
 }
+
+// ---- E9: is the constant-bank variant limited by the uniform loads?  Each loaded sphere is used for REUSE ray pairs
+//      (RP = REUSE here, but only one LDCU per sphere): if tests/s per FFMA2 rises with REUSE, LDCU was the limiter.
+template<int RP>
+__global__ void __launch_bounds__(256) k_scan8_const_ur(float* out, int n, int iters){
+  float2 dx[RP],dy[RP],dz[RP],m2ox[RP],m2oy[RP],m2oz[RP],nod[RP],oo[RP]; unsigned acc=0;
+  #pragma unroll
+  for(int r=0;r<RP;r++){ float t=(threadIdx.x*RP+r)*0.01f; float2 ox=make_float2(13+t,13-t), oy=make_float2(2,2.1f), oz=make_float2(3-t,3+t);
+    dx[r]=make_float2(-0.9f+t*1e-3f,-0.9f-t*1e-3f); dy[r]=make_float2(-0.1f+t*0.01f,-0.1f); dz[r]=make_float2(-0.2f-t*1e-3f,-0.2f+t*1e-3f);
+    m2ox[r]=make_float2(-2*ox.x,-2*ox.y); m2oy[r]=make_float2(-2*oy.x,-2*oy.y); m2oz[r]=make_float2(-2*oz.x,-2*oz.y);
+    nod[r]=make_float2(-(ox.x*dx[r].x+oy.x*dy[r].x+oz.x*dz[r].x),-(ox.y*dx[r].y+oy.y*dy[r].y+oz.y*dz[r].y));
+    oo[r]=make_float2(ox.x*ox.x+oy.x*oy.x+oz.x*oz.x, ox.y*ox.y+oy.y*oy.y+oz.y*oz.y); }
+  for(int it=0; it<iters; ++it){
+    for(int w=0; w<n; w+=16){
+      unsigned m0[RP], m1[RP];
+      #pragma unroll
+      for(int r=0;r<RP;r++){ m0[r]=0; m1[r]=0; }
+      #pragma unroll
+      for(int q=0;q<16;q++){
+        float4 s=c_sph[w+q];
+        #pragma unroll
+        for(int r=0;r<RP;r++){
+          float2 hb=ffma2(bc(s.x),dx[r],ffma2(bc(s.y),dy[r],ffma2(bc(s.z),dz[r],nod[r])));
+          float2 C=ffma2(bc(s.x),m2ox[r],ffma2(bc(s.y),m2oy[r],ffma2(bc(s.z),m2oz[r],fadd2(bc(s.w),oo[r]))));
+          float2 disc=ffma2(hb,hb,neg2(C));
+          m0[r]=__funnelshift_l(__float_as_uint(disc.x), m0[r], 1);
+          m1[r]=__funnelshift_l(__float_as_uint(disc.y), m1[r], 1);
+        }
+      }
+      #pragma unroll
+      for(int r=0;r<RP;r++){ acc+=__popc(~m0[r])+__popc(~m1[r]); oo[r].x+=1e-6f; }
+    }
+  }
+  out[blockIdx.x*blockDim.x+threadIdx.x]=acc;
+}
 static float time_ms(cudaEvent_t a, cudaEvent_t b){ float ms; CK(cudaEventElapsedTime(&ms,a,b)); return ms; }
 
 int main(int argc, char** argv){
@@ -512,6 +547,8 @@ int main(int argc, char** argv){
   SCAN("scan8_opmajor_8",(k_scan8_opmajor<8><<<ctas,threads,smem>>>(g,out,n,sit)),1);
   SCAN("scan8_const_RP1",(k_scan8_const<1><<<ctas,threads>>>(out,n,sit)),2);
   SCAN("scan8_const_RP2",(k_scan8_const<2><<<ctas,threads>>>(out,n,sit)),4);
+  SCAN("scan8_constur_RP1",(k_scan8_const_ur<1><<<ctas,threads>>>(out,n,sit)),2);
+  SCAN("scan8_constur_RP3",(k_scan8_const_ur<3><<<ctas,threads>>>(out,n,sit)),6);
   SCAN("scan8_pf1",(k_scan_smem8_pf<1><<<ctas,threads,smem>>>(g,out,n,sit)),1);
   SCAN("scan8_pf2",(k_scan_smem8_pf<2><<<ctas,threads,smem>>>(g,out,n,sit)),1);
   SCAN("scan8_pf3",(k_scan_smem8_pf<3><<<ctas,threads,smem>>>(g,out,n,sit)),1);
