@@ -381,6 +381,16 @@ template <typename K> static int prep_kernel(K kernel, size_t smem, int threads,
     return RTIOW_OK;
 }
 
+// chunks handed out per atomic: up to 256 samples' worth, but small frames get smaller fetches so that every warp of the
+// persistent grid still draws >= 8 of them (a 400x225@10 frame is only ~6 paths per lane: big fetches left warps idle)
+template <typename T> static void size_fetch(RenderArgs<T>& a, int grid, int threads)
+{
+    const uint64_t n_warps = (uint64_t)grid * threads / 32;
+    const uint64_t want = a.n_chunks / std::max<uint64_t>(1, n_warps * 8);
+    const uint64_t cap = std::max<uint32_t>(1u, 256u / a.chunk_samples);
+    a.chunks_per_fetch = (uint32_t)std::min<uint64_t>(cap, std::max<uint64_t>(1, want));
+}
+
 template <typename T>
 static int launch_render(DeviceState& d, const rtiow_camera* cam, const rtiow_params* p, uint32_t rank, uint32_t world, uint32_t* d_tiles,
                          cudaStream_t st, uint32_t* launches, bool cull_ok, uint32_t* peer_frame)
@@ -405,6 +415,7 @@ static int launch_render(DeviceState& d, const rtiow_camera* cam, const rtiow_pa
     if (sizeof(T) == 8) {
         auto k = render_kernel<T, false, 256, 2>;
         int rc = prep_kernel(k, 0, 256, d.sms, &grid); if (rc) return rc;
+        size_fetch(a, grid, 256);
         k<<<grid, 256, 0, st>>>(a);
     } else {
         const ScanCfg cfg = pick_cfg(d.scene.np);
@@ -413,22 +424,27 @@ static int launch_render(DeviceState& d, const rtiow_camera* cam, const rtiow_pa
         if (cfg.variant == 0 && min_ctas == 3) {
             auto k = render_kernel<T, true, 256, 3>;
             int rc = prep_kernel(k, cfg.smem, 256, d.sms, &grid); if (rc) return rc;
+            size_fetch(a, grid, 256);
             k<<<grid, 256, cfg.smem, st>>>(a);
         } else if (cfg.variant == 0 && min_ctas == 2) {
             auto k = render_kernel<T, true, 256, 2>;
             int rc = prep_kernel(k, cfg.smem, 256, d.sms, &grid); if (rc) return rc;
+            size_fetch(a, grid, 256);
             k<<<grid, 256, cfg.smem, st>>>(a);
         } else if (cfg.variant == 0) {
             auto k = render_kernel<T, true, 256, 4>;
             int rc = prep_kernel(k, cfg.smem, 256, d.sms, &grid); if (rc) return rc;
+            size_fetch(a, grid, 256);
             k<<<grid, 256, cfg.smem, st>>>(a);
         } else if (cfg.variant == 1) {
             auto k = render_kernel<T, true, 512, 1>;
             int rc = prep_kernel(k, cfg.smem, 512, d.sms, &grid); if (rc) return rc;
+            size_fetch(a, grid, 512);
             k<<<grid, 512, cfg.smem, st>>>(a);
         } else {
             auto k = render_kernel<T, false, 256, 4>;
             int rc = prep_kernel(k, cfg.smem, 256, d.sms, &grid); if (rc) return rc;
+            size_fetch(a, grid, 256);
             k<<<grid, 256, cfg.smem, st>>>(a);
         }
     }
