@@ -73,26 +73,13 @@ template <typename T> __device__ __forceinline__ void start_ray(PathState<T>& ps
     ps.tmin_n = t_min * len;                        // t is measured in |dir| units (Appendix C.3)
 }
 
-// One iteration of ray_color (main.rs:38-57) for every lane of the warp: world.hit, then the miss /
-// scatter / absorb branches.  Lanes with active == false still take part in the scan (its warp-level
-// operations need all 32) but ignore the result.  Returns the lane's new `active`; when the path ends,
-// *radiance receives its value (throughput x sky, or black).
-template <typename T, bool kSmem>
-__device__ __forceinline__ bool bounce_step(const SceneDev& sc, const float* soa, uint16_t* cand, int cand_stride, uint64_t seed, T t_min,
-                                            bool active, PathState<T>& ps, V3<T>* radiance, uint32_t* n_rays)
+// The part of ray_color (main.rs:38-57) that follows world.hit: the miss / scatter / absorb branches for one lane.
+// (t_hit, idx, code) is the closest hit of the lane's ray (idx < 0: none).  Returns the lane's new `active`; when the path
+// ends, *radiance receives its value (throughput x sky, or black).
+template <typename T>
+__device__ __forceinline__ bool shade_step(const SceneDev& sc, uint64_t seed, T t_min, bool active, PathState<T>& ps, T t_hit, int idx, int code,
+                                           V3<T>* radiance, uint32_t* n_rays)
 {
-    T t_hit; int idx, code;
-    if (sizeof(T) == 4) {                                                     // world.hit(r, t_min, INFINITY), main.rs:44
-        const HitF h = closest_hit<kSmem>(sc, soa, mk<float>((float)ps.o.x, (float)ps.o.y, (float)ps.o.z),
-                                          mk<float>((float)ps.dhat.x, (float)ps.dhat.y, (float)ps.dhat.z), (float)ps.tmin_n, ps.self_code,
-                                          mk<float>((float)ps.self_n.x, (float)ps.self_n.y, (float)ps.self_n.z), cand, cand_stride);
-        t_hit = (T)h.t; idx = h.idx; code = h.code;
-    } else {
-        double td;
-        closest_hit_f64(sc, mk<double>(ps.o.x, ps.o.y, ps.o.z), mk<double>(ps.dhat.x, ps.dhat.y, ps.dhat.z), (double)ps.tmin_n, ps.self_code,
-                        mk<double>(ps.self_n.x, ps.self_n.y, ps.self_n.z), &td, &idx);
-        t_hit = (T)td; code = idx;
-    }
     if (!active) return false;
     ++*n_rays;
     if (idx < 0) {                                                            // miss: sky (main.rs:54-56)
@@ -134,6 +121,99 @@ __device__ __forceinline__ bool bounce_step(const SceneDev& sc, const float* soa
     return true;
 }
 
+// One iteration of ray_color (main.rs:38-57) for every lane of the warp: world.hit, then shade_step.  Lanes with
+// active == false still take part in the scan (its warp-level operations need all 32) but ignore the result.
+template <typename T, bool kSmem>
+__device__ __forceinline__ bool bounce_step(const SceneDev& sc, const float* soa, uint16_t* cand, int cand_stride, uint64_t seed, T t_min,
+                                            bool active, PathState<T>& ps, V3<T>* radiance, uint32_t* n_rays)
+{
+    T t_hit; int idx, code;
+    if (sizeof(T) == 4) {                                                     // world.hit(r, t_min, INFINITY), main.rs:44
+        const HitF h = closest_hit<kSmem>(sc, soa, mk<float>((float)ps.o.x, (float)ps.o.y, (float)ps.o.z),
+                                          mk<float>((float)ps.dhat.x, (float)ps.dhat.y, (float)ps.dhat.z), (float)ps.tmin_n, ps.self_code,
+                                          mk<float>((float)ps.self_n.x, (float)ps.self_n.y, (float)ps.self_n.z), cand, cand_stride);
+        t_hit = (T)h.t; idx = h.idx; code = h.code;
+    } else {
+        double td;
+        closest_hit_f64(sc, mk<double>(ps.o.x, ps.o.y, ps.o.z), mk<double>(ps.dhat.x, ps.dhat.y, ps.dhat.z), (double)ps.tmin_n, ps.self_code,
+                        mk<double>(ps.self_n.x, ps.self_n.y, ps.self_n.z), &td, &idx);
+        t_hit = (T)td; code = idx;
+    }
+    return shade_step<T>(sc, seed, t_min, active, ps, t_hit, idx, code, radiance, n_rays);
+}
+
+// ---- the pixel/sample loop's bookkeeping (main.rs:122-135), shared by the render kernels ------------------------------
+// warp-uniform cursor over the work: chunks (<= 256 samples of ONE pixel) fetched from a global atomic counter
+struct WorkCursor {
+    uint32_t cs = 0, ce = 0, c_lp = 0, c_x = 0, c_y = 0;
+    unsigned long long cc = 0, cce = 0;
+    bool exhausted = false;
+};
+
+template <typename T> __device__ __forceinline__ void init_path(PathState<T>& ps)
+{
+    ps.o = mk<T>(0, 0, 0); ps.dhat = mk<T>(0, 1, 0); ps.thr = mk<T>(0, 0, 0); ps.self_n = mk<T>(0, 1, 0);
+    ps.tmin_n = T(0); ps.self_code = RT_SELF_NONE; ps.pix_key = 0; ps.smp = 0; ps.bounce = 0; ps.depth = 0;
+}
+
+// regeneration: every lane whose path slot is idle starts the next (pixel, sample) of the warp's chunk (main.rs:130-134)
+template <typename T>
+__device__ __forceinline__ void regenerate(const RenderArgs<T>& a, WorkCursor& wc, unsigned lane, unsigned lt_mask, bool& active, PathState<T>& ps,
+                                           uint32_t& acc_lp)
+{
+    unsigned need = __ballot_sync(RT_FULL, !active);
+    while (need && !wc.exhausted) {
+        if (wc.cs == wc.ce) {
+            if (wc.cc == wc.cce) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(a.work_counter, (unsigned long long)a.chunks_per_fetch);
+                wc.cc = __shfl_sync(RT_FULL, base, 0);
+                wc.cce = wc.cc + a.chunks_per_fetch; if (wc.cce > a.n_chunks) wc.cce = a.n_chunks;
+                if (wc.cc >= a.n_chunks) { wc.exhausted = true; break; }
+            }
+            const unsigned long long c = wc.cc++;
+            wc.c_lp = (uint32_t)(c / a.chunks_per_pixel);
+            const uint32_t part = (uint32_t)(c - (unsigned long long)wc.c_lp * a.chunks_per_pixel);
+            wc.cs = part * a.chunk_samples; wc.ce = min(wc.cs + a.chunk_samples, a.spp);
+            const uint32_t lr = wc.c_lp / a.width;
+            wc.c_x = wc.c_lp - lr * a.width;
+            wc.c_y = local_to_global_row(lr, a.tile_rows, a.world, a.rank);
+        }
+        const uint32_t avail = wc.ce - wc.cs;
+        const uint32_t r = __popc(need & lt_mask);
+        if (!active && r < avail) {
+            acc_lp = wc.c_lp;
+            ps.smp = wc.cs + r;
+            const uint32_t j = a.height - 1u - wc.c_y;              // j = 0 is the bottom row (main.rs:132,141-145)
+            ps.pix_key = j * a.width + wc.c_x;
+            const Uniform4<T> u = event_uniforms<T>(a.seed, ps.pix_key, ps.smp, 0u);
+            const T su = (T(wc.c_x) + u.u0) * a.inv_wm1;             // main.rs:131
+            const T sv = (T(j) + u.u1) * a.inv_hm1;                  // main.rs:132
+            T dx, dy; direct_disk(u.u2, u.u3, &dx, &dy);            // camera.rs:48
+            V3<T> ro, rd; get_ray(a.cam, su, sv, dx, dy, &ro, &rd); // main.rs:134
+            start_ray(ps, ro, rd, a.t_min);
+            ps.thr = mk<T>(1, 1, 1); ps.self_code = RT_SELF_NONE;
+            ps.depth = a.max_depth; ps.bounce = 0;
+            active = ps.depth > 0;                                   // main.rs:40-42
+        }
+        wc.cs += min((uint32_t)__popc(need), avail);
+        need = __ballot_sync(RT_FULL, !active);
+    }
+}
+
+// pixel_color += ray_color (main.rs:135): 32.32 fixed-point RED.ADD.U64 straight into the frame's accumulators
+// (integer adds commute: any order, any GPU count, same bits); black paths add nothing
+template <typename T>
+__device__ __forceinline__ void accumulate(const RenderArgs<T>& a, uint32_t acc_lp, V3<T> rad)
+{
+    if (rad.x != T(0) || rad.y != T(0) || rad.z != T(0)) {
+        const size_t n_lp = (size_t)a.local_rows * a.width;
+        atomicAdd(a.accum + acc_lp, to_fix(rad.x));
+        atomicAdd(a.accum + n_lp + acc_lp, to_fix(rad.y));
+        atomicAdd(a.accum + 2 * n_lp + acc_lp, to_fix(rad.z));
+    }
+}
+
 template <typename T, bool kSmem, int kThreads, int kMinCtas>
 __global__ void __launch_bounds__(kThreads, kMinCtas) render_kernel(const RenderArgs<T> a)
 {
@@ -153,71 +233,20 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) render_kernel(const Render
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
 
-    // ---- per-lane path state ----------------------------------------------------------------
+    // ---- per-lane path state, warp-uniform work cursor ----------------------------------------------
     bool active = false;
-    PathState<T> ps;
-    ps.o = mk<T>(0, 0, 0); ps.dhat = mk<T>(0, 1, 0); ps.thr = mk<T>(0, 0, 0); ps.self_n = mk<T>(0, 1, 0);
-    ps.tmin_n = T(0); ps.self_code = RT_SELF_NONE; ps.pix_key = 0; ps.smp = 0; ps.bounce = 0; ps.depth = 0;
+    PathState<T> ps; init_path(ps);
     uint32_t acc_lp = 0;                                // local pixel of the path in flight
     uint32_t n_rays = 0;
-    // ---- warp-uniform work cursor ---------------------------------------------------------------
-    uint32_t cs = 0, ce = 0, c_lp = 0, c_x = 0, c_y = 0;
-    unsigned long long cc = 0, cce = 0;
-    bool exhausted = false;
-    const uint32_t n_lp_stride = a.local_rows * a.width;
+    WorkCursor wc;
 
     for (;;) {
-        // ---- regeneration: idle lanes start the next path (main.rs:130-134) ------------------------
-        unsigned need = __ballot_sync(RT_FULL, !active);
-        while (need && !exhausted) {
-            if (cs == ce) {
-                if (cc == cce) {
-                    unsigned long long base = 0;
-                    if (lane == 0) base = atomicAdd(a.work_counter, (unsigned long long)a.chunks_per_fetch);
-                    cc = __shfl_sync(RT_FULL, base, 0);
-                    cce = cc + a.chunks_per_fetch; if (cce > a.n_chunks) cce = a.n_chunks;
-                    if (cc >= a.n_chunks) { exhausted = true; break; }
-                }
-                const unsigned long long c = cc++;
-                c_lp = (uint32_t)(c / a.chunks_per_pixel);
-                const uint32_t part = (uint32_t)(c - (unsigned long long)c_lp * a.chunks_per_pixel);
-                cs = part * a.chunk_samples; ce = min(cs + a.chunk_samples, a.spp);
-                const uint32_t lr = c_lp / a.width;
-                c_x = c_lp - lr * a.width;
-                c_y = local_to_global_row(lr, a.tile_rows, a.world, a.rank);
-            }
-            const uint32_t avail = ce - cs;
-            const uint32_t r = __popc(need & lt_mask);
-            if (!active && r < avail) {
-                acc_lp = c_lp;
-                ps.smp = cs + r;
-                const uint32_t j = a.height - 1u - c_y;                 // j = 0 is the bottom row (main.rs:132,141-145)
-                ps.pix_key = j * a.width + c_x;
-                const Uniform4<T> u = event_uniforms<T>(a.seed, ps.pix_key, ps.smp, 0u);
-                const T su = (T(c_x) + u.u0) * a.inv_wm1;                // main.rs:131
-                const T sv = (T(j) + u.u1) * a.inv_hm1;                  // main.rs:132
-                T dx, dy; direct_disk(u.u2, u.u3, &dx, &dy);            // camera.rs:48
-                V3<T> ro, rd; get_ray(a.cam, su, sv, dx, dy, &ro, &rd); // main.rs:134
-                start_ray(ps, ro, rd, a.t_min);
-                ps.thr = mk<T>(1, 1, 1); ps.self_code = RT_SELF_NONE;
-                ps.depth = a.max_depth; ps.bounce = 0;
-                active = ps.depth > 0;                                   // main.rs:40-42
-            }
-            cs += min((uint32_t)__popc(need), avail);
-            need = __ballot_sync(RT_FULL, !active);
-        }
+        regenerate(a, wc, lane, lt_mask, active, ps, acc_lp);
         if (!__any_sync(RT_FULL, active)) break;
-
         V3<T> rad = mk<T>(0, 0, 0);
         const bool was = active;
         active = bounce_step<T, kSmem>(a.scene, soa, cand, kThreads, a.seed, a.t_min, active, ps, &rad, &n_rays);
-        // pixel_color += ray_color (main.rs:135): 32.32 fixed-point RED.ADD.U64 straight into the frame's accumulators
-        // (integer adds commute: any order, any GPU count, same bits); black paths add nothing
-        if (was && !active && (rad.x != T(0) || rad.y != T(0) || rad.z != T(0))) {
-            atomicAdd(a.accum + acc_lp, to_fix(rad.x));
-            atomicAdd(a.accum + n_lp_stride + acc_lp, to_fix(rad.y));
-            atomicAdd(a.accum + 2 * (size_t)n_lp_stride + acc_lp, to_fix(rad.z));
-        }
+        if (was && !active) accumulate(a, acc_lp, rad);
     }
     // rays traced by this warp -> one atomic (world.hit call count, main.rs:44)
     uint32_t wr = __reduce_add_sync(RT_FULL, n_rays);
