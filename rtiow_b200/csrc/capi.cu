@@ -69,7 +69,7 @@ struct DeviceState {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_done = nullptr;
     // scene
-    DevBuf<float> soa; DevBuf<float4> small; DevBuf<int> small_idx; DevBuf<double4> big; DevBuf<int> big_idx;
+    DevBuf<float> table; DevBuf<float4> small; DevBuf<int> small_idx; DevBuf<double4> big; DevBuf<int> big_idx;
     DevBuf<float4> sph; DevBuf<double4> sphd; DevBuf<float4> mat; DevBuf<double4> matd; DevBuf<uint8_t> kind;
     SceneDev scene{};
     bool has_scene = false;
@@ -86,20 +86,7 @@ struct rtiow_ctx {
     std::vector<DeviceState> dev;
     size_t scene_bytes = 0;
     bool peer_ok = true;                 // every device can store into device 0's memory (NVLink P2P): fused epilogue + gather
-    std::vector<float4> host_small;      // the culled segment's spheres (cx,cy,cz,r; r = 0 for padding): origin-inside checks
 };
-
-// true if a point (with a safety radius) lies inside or on any sphere of the culled segment: then behind-the-ray culling
-// must be switched off for the call (SceneDev::w_cull = 0), because a ray leaving the INSIDE of a sphere hits it from behind
-static bool origin_inside_culled(const rtiow_ctx* c, double x, double y, double z, double pad)
-{
-    for (const float4& s : c->host_small) {
-        if (s.w == 0.0f) continue;
-        const double dx = x - s.x, dy = y - s.y, dz = z - s.z, r = std::fabs((double)s.w) * (1.0 + 1e-5) + pad;
-        if (dx * dx + dy * dy + dz * dz <= r * r) return true;
-    }
-    return false;
-}
 
 static int init_device(DeviceState& d, int device)
 {
@@ -160,7 +147,7 @@ extern "C" void rtiow_ctx_destroy(rtiow_ctx* c)
     for (auto& d : c->dev) {
         cudaSetDevice(d.device);
         if (d.stream) cudaStreamSynchronize(d.stream);
-        d.soa.release(); d.small.release(); d.small_idx.release(); d.big.release(); d.big_idx.release();
+        d.table.release(); d.small.release(); d.small_idx.release(); d.big.release(); d.big_idx.release();
         d.sph.release(); d.sphd.release(); d.mat.release(); d.matd.release(); d.kind.release();
         d.accum.release(); d.counters.release(); d.tiles.release(); d.gathered.release(); d.frame.release();
         d.flush.release(); d.probe.release();
@@ -207,59 +194,54 @@ extern "C" int rtiow_scene_upload(rtiow_ctx* c, const rtiow_spheres* s, const rt
         if (std::fabs(s->radius[i]) > kBigRadius || reach > 4096.0) big_ids.push_back(i); else small_ids.push_back(i);
     }
     const int ns = (int)small_ids.size(), nb = (int)big_ids.size();
-    // Split the small spheres: those that overlap NO other sphere can contain no ray origin (origins are scatter points on
-    // some sphere's surface, or the camera — checked per render), so the filter may cull them when they lie behind the ray
-    // (filter_word<true>).  Overlapping / nested spheres (hollow glass: r=1 and r=-0.9, BASELINE configs[2]) keep the plain filter.
-    // O(n^2) on the f32-rounded spheres, a few 1e7 pair tests at 10 k spheres.
-    std::vector<char> overlaps(n, 0);
-    {
-        const double tol = 1e-5;
-        for (int i = 0; i < n; ++i)
-            for (int j = i + 1; j < n; ++j) {
-                const double dx = (double)sph[i].x - sph[j].x, dy = (double)sph[i].y - sph[j].y, dz = (double)sph[i].z - sph[j].z;
-                const double rs = std::fabs((double)sph[i].w) + std::fabs((double)sph[j].w) + tol;
-                if (dx * dx + dy * dy + dz * dz < rs * rs) { overlaps[i] = 1; overlaps[j] = 1; }
-            }
-    }
-    std::vector<int> order; order.reserve(ns + 64);
-    for (int id : small_ids) if (!overlaps[id]) order.push_back(id);
-    const int np_cull = (int)order.size() / 32 * 32;       // whole words only; the mixed word is filtered without culling
-    for (int id : small_ids) if (overlaps[id]) order.push_back(id);
+    std::vector<int> order(small_ids);
     while (order.size() % 32) order.push_back(-1);
     const int np = (int)order.size();
     if (np > 65535 * 32) return fail(RTIOW_ERR_UNSUPPORTED, "scene too large");
-    std::vector<float> soa((size_t)4 * np); std::vector<float4> small(np); std::vector<int> small_idx(np);
+    // R: radius of the sphere around the coordinate origin on which the filter places its line point (rt_scene.cuh);
+    // it bounds every small sphere, so a line that misses it can hit none of them
+    double R = 1.0, rmax = 0.0;
+    for (int id : small_ids) {
+        const float4 v = sph[id];
+        R = std::max(R, std::sqrt((double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z) + std::fabs((double)v.w));
+        rmax = std::max(rmax, std::fabs((double)v.w));
+    }
+    const float R2f = (float)(R * R * (1.0 + 1e-6));
+    const double R2 = (double)R2f;
+    std::vector<float> table(RT_TABLE_FLOATS(np), 0.0f); std::vector<float4> small(np); std::vector<int> small_idx(np);
     for (int p = 0; p < np; ++p) {
+        float* rec = table.data() + (size_t)(p >> 2) * 16 + (p & 3);          // record of 4 spheres: [cx0..3][cy0..3][cz0..3][K0..3]
         if (order[p] >= 0) {
             const float4 v = sph[order[p]];
-            soa[p] = v.x; soa[np + p] = v.y; soa[2 * (size_t)np + p] = v.z;
-            // K = |c|^2 - r^2 of the f32 sphere, in f64, lowered by the filter slack (RT_FILTER_SLACK, rt_scene.cuh)
+            rec[0] = v.x; rec[4] = v.y; rec[8] = v.z;
+            // K = |c|^2 - r^2 + R^2 of the f32 sphere, in f64, lowered by the filter slack (RT_FILTER_SLACK, rt_scene.cuh)
             // and rounded toward -inf: the filter may only err towards keeping a sphere
             const double c2 = (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z, r2 = (double)v.w * v.w;
-            const double K = c2 - r2 - (double)RT_FILTER_SLACK * (c2 + r2) - 1e-30;
+            const double K = c2 - r2 + R2 - (double)RT_FILTER_SLACK * (c2 + r2 + R2) - 1e-30;
             float Kf = (float)K; if ((double)Kf > K) Kf = std::nextafterf(Kf, -INFINITY);
-            soa[3 * (size_t)np + p] = Kf;
+            rec[12] = Kf;
             small[p] = v; small_idx[p] = order[p];
         } else {       // padding: C = 1e30 can never be reached by hb^2
-            soa[p] = 0; soa[np + p] = 0; soa[2 * (size_t)np + p] = 0; soa[3 * (size_t)np + p] = 1e30f;
+            rec[0] = 0; rec[4] = 0; rec[8] = 0; rec[12] = 1e30f;
             small[p] = make_float4(0, 0, 0, 0); small_idx[p] = -1;
         }
     }
-    c->host_small.assign(small.begin(), small.begin() + np_cull);
+    for (int k = 0; k < 4; ++k) table[(size_t)np * 4 + 12 + k] = 1e30f;        // the look-ahead record: never hit, never used
     std::vector<double4> big(nb); for (int b = 0; b < nb; ++b) big[b] = sphd[big_ids[b]];
     c->scene_bytes = 0;
     for (auto& d : c->dev) {
         CU(cudaSetDevice(d.device));
-        CU(d.soa.resize(soa.size())); CU(d.small.resize(np)); CU(d.small_idx.resize(np)); CU(d.big.resize(nb)); CU(d.big_idx.resize(nb));
+        CU(d.table.resize(table.size())); CU(d.small.resize(np)); CU(d.small_idx.resize(np)); CU(d.big.resize(nb)); CU(d.big_idx.resize(nb));
         CU(d.sph.resize(n)); CU(d.sphd.resize(n)); CU(d.mat.resize(n)); CU(d.matd.resize(n)); CU(d.kind.resize(n));
         size_t bytes = 0;
 #define UP(dst, src, cnt, type) do { if ((cnt) > 0) { CU(cudaMemcpyAsync(dst.p, src.data(), (size_t)(cnt) * sizeof(type), cudaMemcpyHostToDevice, d.stream)); bytes += (size_t)(cnt) * sizeof(type); } } while (0)
-        UP(d.soa, soa, soa.size(), float); UP(d.small, small, np, float4); UP(d.small_idx, small_idx, np, int);
+        UP(d.table, table, table.size(), float); UP(d.small, small, np, float4); UP(d.small_idx, small_idx, np, int);
         UP(d.big, big, nb, double4); UP(d.big_idx, big_ids, nb, int);
         UP(d.sph, sph, n, float4); UP(d.sphd, sphd, n, double4); UP(d.mat, mat, n, float4); UP(d.matd, matd, n, double4); UP(d.kind, kind, n, uint8_t);
 #undef UP
         CU(cudaStreamSynchronize(d.stream));
-        d.scene.soa = d.soa.p; d.scene.small = d.small.p; d.scene.small_idx = d.small_idx.p; d.scene.np = np; d.scene.w_cull = np_cull / 32;
+        d.scene.table = d.table.p; d.scene.small = d.small.p; d.scene.small_idx = d.small_idx.p; d.scene.np = np;
+        d.scene.filter_R2 = R2f; d.scene.filter_sigma = (float)(16.0 * 5.9604644775390625e-08 * std::max(rmax, 1e-3));
         d.scene.big = d.big.p; d.scene.big_idx = d.big_idx.p; d.scene.nb = nb;
         d.scene.sph = d.sph.p; d.scene.sphd = d.sphd.p; d.scene.mat = d.mat.p; d.scene.matd = d.matd.p; d.scene.kind = d.kind.p; d.scene.n = n;
         d.has_scene = true;
@@ -365,9 +347,9 @@ struct ScanCfg { int variant; size_t smem; };   // 0: smem 256x4, 1: smem 512x1 
 static size_t cand_bytes(int threads) { return (size_t)threads * RT_CAND_CAP * sizeof(uint16_t); }
 static ScanCfg pick_cfg(int np)
 {
-    const size_t soa = (size_t)np * 16;
-    if (soa + cand_bytes(256) <= 56 * 1024) return { 0, soa + cand_bytes(256) };
-    if (soa + cand_bytes(512) <= 227 * 1024) return { 1, soa + cand_bytes(512) };
+    const size_t table = RT_TABLE_FLOATS(np) * sizeof(float);
+    if (table + cand_bytes(256) <= 56 * 1024) return { 0, table + cand_bytes(256) };
+    if (table + cand_bytes(512) <= 227 * 1024) return { 1, table + cand_bytes(512) };
     return { 2, cand_bytes(256) };
 }
 
@@ -393,11 +375,10 @@ template <typename T> static void size_fetch(RenderArgs<T>& a, int grid, int thr
 
 template <typename T>
 static int launch_render(DeviceState& d, const rtiow_camera* cam, const rtiow_params* p, uint32_t rank, uint32_t world, uint32_t* d_tiles,
-                         cudaStream_t st, uint32_t* launches, bool cull_ok, uint32_t* peer_frame)
+                         cudaStream_t st, uint32_t* launches, uint32_t* peer_frame)
 {
     RenderArgs<T> a;
     a.scene = d.scene; a.cam = to_dev_camera<T>(*cam);
-    if (!cull_ok) a.scene.w_cull = 0;                 // the camera lens touches a sphere of the culled segment
     a.width = p->width; a.height = p->height; a.spp = p->spp; a.max_depth = p->max_depth; a.t_min = (T)p->t_min; a.seed = p->seed;
     a.inv_wm1 = (T)(1.0 / (double)(p->width - 1)); a.inv_hm1 = (T)(1.0 / (double)(p->height - 1));
     a.rank = rank; a.world = world; a.tile_rows = p->tile_rows; a.local_rows = rows_of_rank(p->height, p->tile_rows, world, rank);
@@ -461,11 +442,10 @@ static int launch_render(DeviceState& d, const rtiow_camera* cam, const rtiow_pa
 static int render_tiles(const rtiow_ctx* c, DeviceState& d, const rtiow_camera* cam, const rtiow_params* p, uint32_t rank, uint32_t world, uint32_t* d_tiles,
                         cudaStream_t st, uint32_t* launches, uint32_t* peer_frame = nullptr)
 {
-    const bool cull_ok = !origin_inside_culled(c, cam->origin[0], cam->origin[1], cam->origin[2], std::fabs(cam->lens_radius) * 1.001 + 1e-6);
     if (!d.has_scene) return fail(RTIOW_ERR_INVALID_ARG, "no scene uploaded (call rtiow_scene_upload first)");
     CU(cudaSetDevice(d.device));
-    return p->precision == RTIOW_PRECISION_F64 ? launch_render<double>(d, cam, p, rank, world, d_tiles, st, launches, cull_ok, peer_frame)
-                                               : launch_render<float>(d, cam, p, rank, world, d_tiles, st, launches, cull_ok, peer_frame);
+    return p->precision == RTIOW_PRECISION_F64 ? launch_render<double>(d, cam, p, rank, world, d_tiles, st, launches, peer_frame)
+                                               : launch_render<float>(d, cam, p, rank, world, d_tiles, st, launches, peer_frame);
 }
 
 static double now_ms()
@@ -654,7 +634,6 @@ extern "C" int rtiow_hitlist_batch(rtiow_ctx* c, int precision, int64_t n, const
     if (!d.has_scene) return fail(RTIOW_ERR_INVALID_ARG, "no scene uploaded");
     if (n == 0) return RTIOW_OK;
     SceneDev scene = d.scene;
-    for (int64_t i = 0; i < n && scene.w_cull; ++i) if (origin_inside_culled(c, orig[3 * i], orig[3 * i + 1], orig[3 * i + 2], 1e-6)) scene.w_cull = 0;
     double *dor, *dd, *dt, *dp, *dn; int32_t *dh, *di, *dff;
     CU(S.in(orig, N3, &dor)); CU(S.in(dir, N3, &dd));
     CU(S.out(n, &dh)); CU(S.out(n, &di)); CU(S.out(n, &dt)); CU(S.out(N3, &dp)); CU(S.out(N3, &dn)); CU(S.out(n, &dff));
@@ -763,7 +742,6 @@ extern "C" int rtiow_ray_color_batch(rtiow_ctx* c, int precision, int64_t n, con
     if (!d.has_scene) return fail(RTIOW_ERR_INVALID_ARG, "no scene uploaded");
     if (n == 0) return RTIOW_OK;
     SceneDev scene = d.scene;
-    for (int64_t i = 0; i < n && scene.w_cull; ++i) if (origin_inside_culled(c, orig[3 * i], orig[3 * i + 1], orig[3 * i + 2], 1e-6)) scene.w_cull = 0;
     double *dor, *dd, *dcol; uint32_t *dpx, *dsm; unsigned long long* dr;
     CU(S.in(orig, N3, &dor)); CU(S.in(dir, N3, &dd)); CU(S.in(pixel, n, &dpx)); CU(S.in(sample, n, &dsm));
     CU(S.out(N3, &dcol)); CU(S.out(n, &dr));

@@ -124,12 +124,12 @@ __device__ __forceinline__ bool shade_step(const SceneDev& sc, uint64_t seed, T 
 // One iteration of ray_color (main.rs:38-57) for every lane of the warp: world.hit, then shade_step.  Lanes with
 // active == false still take part in the scan (its warp-level operations need all 32) but ignore the result.
 template <typename T, bool kSmem>
-__device__ __forceinline__ bool bounce_step(const SceneDev& sc, const float* soa, uint16_t* cand, int cand_stride, uint64_t seed, T t_min,
+__device__ __forceinline__ bool bounce_step(const SceneDev& sc, const float* table, uint16_t* cand, int cand_stride, uint64_t seed, T t_min,
                                             bool active, PathState<T>& ps, V3<T>* radiance, uint32_t* n_rays)
 {
     T t_hit; int idx, code;
     if (sizeof(T) == 4) {                                                     // world.hit(r, t_min, INFINITY), main.rs:44
-        const HitF h = closest_hit<kSmem>(sc, soa, mk<float>((float)ps.o.x, (float)ps.o.y, (float)ps.o.z),
+        const HitF h = closest_hit<kSmem>(sc, table, mk<float>((float)ps.o.x, (float)ps.o.y, (float)ps.o.z),
                                           mk<float>((float)ps.dhat.x, (float)ps.dhat.y, (float)ps.dhat.z), (float)ps.tmin_n, ps.self_code,
                                           mk<float>((float)ps.self_n.x, (float)ps.self_n.y, (float)ps.self_n.z), cand, cand_stride);
         t_hit = (T)h.t; idx = h.idx; code = h.code;
@@ -218,14 +218,14 @@ template <typename T, bool kSmem, int kThreads, int kMinCtas>
 __global__ void __launch_bounds__(kThreads, kMinCtas) render_kernel(const RenderArgs<T> a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* s_soa = reinterpret_cast<float*>(smem_raw);
+    float* s_table = reinterpret_cast<float*>(smem_raw);
     const int np = a.scene.np;
-    const float* soa = a.scene.soa;
+    const float* table = a.scene.table;
     uint16_t* cand_base;
     if (kSmem) {
-        stage_scene(s_soa, a.scene.soa, np);
-        soa = s_soa;
-        cand_base = reinterpret_cast<uint16_t*>(s_soa + 4 * (size_t)np);
+        stage_scene(s_table, a.scene.table, np);
+        table = s_table;
+        cand_base = reinterpret_cast<uint16_t*>(s_table + RT_TABLE_FLOATS(np));
     } else {
         cand_base = reinterpret_cast<uint16_t*>(smem_raw);
     }
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) render_kernel(const Render
         if (!__any_sync(RT_FULL, active)) break;
         V3<T> rad = mk<T>(0, 0, 0);
         const bool was = active;
-        active = bounce_step<T, kSmem>(a.scene, soa, cand, kThreads, a.seed, a.t_min, active, ps, &rad, &n_rays);
+        active = bounce_step<T, kSmem>(a.scene, table, cand, kThreads, a.seed, a.t_min, active, ps, &rad, &n_rays);
         if (was && !active) accumulate(a, acc_lp, rad);
     }
     // rays traced by this warp -> one atomic (world.hit call count, main.rs:44)

@@ -2,9 +2,11 @@
 // /root/reference/src/shapes/mod.rs:56-69) of the B200 render path.
 //
 // Layout in HBM (built once by rtiow_scene_upload, read-only afterwards):
-//   soa      float [4][np]   cx | cy | cz | K     "small" spheres in list order, padded to a multiple
-//                            of 32 with never-hit entries; staged into shared memory by each CTA and
-//                            streamed as broadcast LDS.128 (4 spheres per load per array)
+//   table    float [np/4+1][4][4]  filter table: one 64-byte record per 4 "small" spheres,
+//                            [cx0..3][cy0..3][cz0..3][K0..3], K = |c|^2 - r^2 + R^2 lowered by the filter slack; list
+//                            order, padded to whole 32-sphere words with never-hit entries (+1 record for the
+//                            pipeline's look-ahead); staged into shared memory by each CTA and streamed as broadcast
+//                            LDS.128 (4 spheres per load)
 //   small    float4 [np]     (cx, cy, cz, r) exact f32 copy for the precise test of candidates
 //   small_idx int   [np]     position in `small` -> index in the reference's list (-1 = padding)
 //   big      double4 [nb]    (cx, cy, cz, r) spheres whose radius makes |oc|^2 - r^2 cancel in f32
@@ -18,11 +20,12 @@
 namespace rt {
 
 struct SceneDev {
-    const float* soa;
+    const float* table;     // filter table, RT_TABLE_FLOATS(np) floats
     const float4* small;
     const int* small_idx;
     int np;
-    int w_cull;             // 32-sphere words [0, w_cull) may use behind-the-ray culling (rt_scene.cuh, filter_word)
+    float filter_R2;        // R^2: squared radius of the sphere around the coordinate origin that bounds every small sphere
+    float filter_sigma;     // 16 u max|r|: per unit of |origin|_1, how far outside the R-sphere the filter's line point is put
     const double4* big;
     const int* big_idx;
     int nb;
@@ -35,10 +38,10 @@ struct SceneDev {
 };
 
 #define RT_FULL 0xffffffffu
-// Conservative slack of the f32 filter, in units of (|c|^2 + |o|^2): 96 * 2^-24.  The filter's rounding
-// error is bounded by ~40 u (|c|^2 + |o|^2) + 4 u r^2 (u = 2^-24; derivation in DESIGN.md), so with this
-// slack every sphere the precise test can accept passes the filter.  The per-sphere share is folded
-// into K at upload, the per-ray share into |o|^2 below: no cost inside the loop.
+// Conservative slack of the f32 filter, in units of (|c|^2 + r^2 + R^2): 96 * 2^-24.  The filter's rounding
+// error is bounded by ~48 u (|c|^2 + R^2) + 4 u r^2 (u = 2^-24; derivation in DESIGN.md), so with this
+// slack every sphere the precise test can accept passes the filter.  It is folded into K at upload: no cost
+// inside the loop.
 #define RT_FILTER_SLACK 5.7220458984375e-06f
 #define RT_CAND_CAP 16           // candidate slots per lane per segment (uint16 positions)
 #define RT_SEG_WORDS 32          // 32 words x 32 spheres per segment between drains
@@ -78,57 +81,76 @@ __device__ __forceinline__ void candidate_self(V3<T> dhat, T inv_a, T t_min, V3<
     if (t < *t_best || (t == *t_best && idx > *i_best)) { *t_best = t; *i_best = idx; }
 }
 
-// The f32 scan over the shared-memory SoA.
-//   filter (all spheres, branch-free, packed f32x2 over sphere pairs), sphere.rs:18-25 expanded around
-//   the coordinate origin so that the per-ray and per-sphere parts separate:
-//       hb = c.d - o.d ;  C = K + |o|^2 - 2 c.o ,  K = |c|^2 - r^2 ;  disc' = hb^2 - C     (8 packed ops per 2 tests)
-//     With K and |o|^2 lowered by RT_FILTER_SLACK, disc' >= 0 is a conservative superset of
-//     "discriminant >= 0" (sphere.rs:24-25); its sign bit is funnel-shifted into a 32-sphere word
-//     (1 SHF per test on the ALU pipe, co-issued).  The expansion cancels |c|^2 + |o|^2 against 2 c.o, which
-//     is why it is only a filter: every survivor goes through the well-conditioned sphere_roots.
-//   candidates (a few per ray): positions appended to a per-lane list in shared memory, then the
-//     whole warp drains its lists in lock-step through candidate<float>.
-// s_soa: [4][np] floats in shared memory (or global when the scene does not fit).
-// Per-ray constants of the filter (rt_scene.cuh header comment): broadcast scalars for the packed ops.
+// The f32 scan over the filter table (shared memory, or global when the scene does not fit).
+//
+//   Filter, all spheres, branch-free, packed f32x2 over sphere pairs: 7 FFMA2 per 2 tests, nothing else on the FP32 pipe.
+//   sphere.rs:18-25 is oc = o - c; half_b = oc.d; c = |oc|^2 - r^2; disc = half_b^2 - a c.  The discriminant belongs to
+//   the ray's LINE, so any point p of the line may stand in for the origin; expanded around the coordinate origin, with
+//   a unit direction,
+//       hb = c.d - p.d ;   C = (|c|^2 - r^2 + |p|^2) - 2 c.p ;   disc' = hb^2 - C .
+//   Per-ray and per-sphere parts separate except for |p|^2 — so p is chosen ON THE SPHERE |p| = R around the coordinate
+//   origin (R = SceneDev::filter_R2^(1/2), a bound of all small spheres, fixed at upload): then |p|^2 = R^2 is a constant
+//   of the scene and is folded into the per-sphere K = |c|^2 - r^2 + R^2 at upload.  What is left per sphere pair is
+//       hb = fma(X, dx, fma(Y, dy, fma(Z, dz, -p.d)))          3 FFMA2
+//       C  = fma(X, -2px, fma(Y, -2py, fma(Z, -2pz, K)))       3 FFMA2   (K is the chain head's addend: no separate add)
+//       disc' = fma(hb, hb, -C)                                1 FFMA2
+//   and one SHF per test (ALU pipe) that funnel-shifts the sign bit of disc' into a 32-sphere word.  B200 issues one
+//   warp instruction per cycle per sub-partition and an FFMA2 holds the issue port for two, so the scan costs
+//   14 + 2 (SHF) + 2 (LDS.128) cycles per sphere pair (tools/probe_ur.cu: 8 ops 60.7, 7 ops 65.8 TFLOP/s-equivalent).
+//   The expansion cancels |c|^2 + R^2 against 2 c.p, which is why it is only a FILTER: K is lowered at upload by
+//   RT_FILTER_SLACK (|c|^2 + r^2 + R^2) and p is placed slightly outside the R-sphere (|p|^2 = R^2 + sigma, sigma covering
+//   the f32 error of the foot point of a distant origin), so disc' >= 0 is a conservative superset of
+//   "discriminant >= 0" (sphere.rs:24-25).  Every survivor goes through the well-conditioned sphere_roots.
+//   A line that misses the R-sphere keeps its foot point (|p| > R: C only gets smaller, still conservative).
+//
+//   Candidates (a few per ray): positions appended to a per-lane list in shared memory, then the whole warp drains its
+//   lists in lock-step through candidate<float>.
+//
+// Table layout: one 64-byte record per 4 spheres, [cx0..3][cy0..3][cz0..3][K0..3], in list order of `small`, padded to whole
+// 32-sphere words with never-hit entries plus ONE extra record (the software pipeline always loads one record ahead).
+// A word is 512 contiguous bytes: every LDS.128 of the unrolled word is [base + immediate].
+#define RT_TABLE_FLOATS(np) (4 * (size_t)(np) + 16)
+
 struct FilterRay {
-    float2 M2OX, M2OY, M2OZ, DX, DY, DZ, NOD, OO;
+    float M2PX, M2PY, M2PZ, DX, DY, DZ, NPD;
 };
-__device__ __forceinline__ FilterRay make_filter_ray(V3<float> o, V3<float> dhat)
+__device__ __forceinline__ FilterRay make_filter_ray(V3<float> o, V3<float> dhat, float inv_a, float R2, float sigma_per_len)
 {
-    FilterRay f;
-    const float oo = length_squared(o);
-    f.M2OX = bc2(-2.0f * o.x); f.M2OY = bc2(-2.0f * o.y); f.M2OZ = bc2(-2.0f * o.z);
-    f.DX = bc2(dhat.x); f.DY = bc2(dhat.y); f.DZ = bc2(dhat.z);
-    f.NOD = bc2(-dot(o, dhat));
-    f.OO = bc2(oo - RT_FILTER_SLACK * oo);
-    return f;
+    // foot point of the coordinate origin on the line, orthogonalised twice: the second pass removes the O(u |o|)
+    // component along dhat that the first leaves when the origin is far away
+    V3<float> f = o - dhat * (dot(o, dhat) * inv_a);
+    f = f - dhat * (dot(f, dhat) * inv_a);
+    const float ff = length_squared(f);
+    // |p|^2 = R^2 + sigma, sigma = 16 u r_max |o|_1: the foot point of a far origin is only known to ~4 u |o|
+    const float sigma = sigma_per_len * (fabsf(o.x) + fabsf(o.y) + fabsf(o.z));
+    const float h2 = (R2 + sigma) - ff;
+    const float s = h2 > 0.0f ? sqrtf(h2 * inv_a) : 0.0f;
+    const V3<float> p = f - dhat * s;                       // where the line enters the R-sphere (or its foot point)
+    FilterRay r;
+    r.M2PX = -2.0f * p.x; r.M2PY = -2.0f * p.y; r.M2PZ = -2.0f * p.z;
+    r.DX = dhat.x; r.DY = dhat.y; r.DZ = dhat.z;
+    r.NPD = -dot(p, dhat);
+    return r;
 }
 
-// One 32-sphere word of the filter.  kCull: the last op is hb*|hb| - C instead of hb*hb - C (the |.| is an operand
-// modifier of FFMA2, so it is free): a sphere whose centre lies BEHIND the ray (hb < 0) then only passes if the origin
-// is deep inside it, i.e. spheres entirely behind an outside origin — about half of all line/sphere intersections of a
-// bounce ray — never become candidates.  Valid only for spheres no ray origin can be inside of (see `n_cull` below).
-template <bool kCull>
-__device__ __forceinline__ unsigned filter_word(const float4* __restrict__ CX, const float4* __restrict__ CY, const float4* __restrict__ CZ,
-                                                const float4* __restrict__ KK, int q0, int q_next_word, const FilterRay& f,
-                                                float4& ncx, float4& ncy, float4& ncz, float4& nkk)
+// One 32-sphere word of the filter: 8 records, software-pipelined one record ahead (the ~30-cycle shared-memory latency
+// hides behind the 14 FFMA2 of the current record).  Bit (31-k) of the result is CLEAR when sphere k passed.
+__device__ __forceinline__ unsigned filter_word(const float4* __restrict__ rec, const FilterRay& f, float4& ncx, float4& ncy, float4& ncz, float4& nkk)
 {
     unsigned m = 0;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const float4 cx = ncx, cy = ncy, cz = ncz, kk = nkk;
-        const int qn = q < 7 ? q0 + q + 1 : q_next_word;
-        ncx = CX[qn]; ncy = CY[qn]; ncz = CZ[qn]; nkk = KK[qn];
+        ncx = rec[4 * q + 4]; ncy = rec[4 * q + 5]; ncz = rec[4 * q + 6]; nkk = rec[4 * q + 7];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const float2 X = h ? make_float2(cx.z, cx.w) : make_float2(cx.x, cx.y);
             const float2 Y = h ? make_float2(cy.z, cy.w) : make_float2(cy.x, cy.y);
             const float2 Z = h ? make_float2(cz.z, cz.w) : make_float2(cz.x, cz.y);
             const float2 K = h ? make_float2(kk.z, kk.w) : make_float2(kk.x, kk.y);
-            const float2 hb = ffma2(X, f.DX, ffma2(Y, f.DY, ffma2(Z, f.DZ, f.NOD)));
-            const float2 C = ffma2(X, f.M2OX, ffma2(Y, f.M2OY, ffma2(Z, f.M2OZ, fadd2(K, f.OO))));
-            const float2 hb2 = kCull ? make_float2(fabsf(hb.x), fabsf(hb.y)) : hb;
-            const float2 disc = ffma2(hb, hb2, neg2(C));
+            const float2 hb = ffma2(X, bc2(f.DX), ffma2(Y, bc2(f.DY), ffma2(Z, bc2(f.DZ), bc2(f.NPD))));
+            const float2 C = ffma2(X, bc2(f.M2PX), ffma2(Y, bc2(f.M2PY), ffma2(Z, bc2(f.M2PZ), K)));
+            const float2 disc = ffma2(hb, hb, neg2(C));
             m = __funnelshift_l(__float_as_uint(disc.x), m, 1);
             m = __funnelshift_l(__float_as_uint(disc.y), m, 1);
         }
@@ -136,37 +158,25 @@ __device__ __forceinline__ unsigned filter_word(const float4* __restrict__ CX, c
     return m;
 }
 
-// words [0, w_cull) hold spheres that provably contain no ray origin (they overlap no other sphere and not the
-// camera lens): filtered with behind-the-ray culling; words [w_cull, n_words) hold the rest, filtered without.
 template <bool kSmem>
-__device__ __forceinline__ void scan_small(const float* __restrict__ s_soa, int np, int w_cull, const float4* __restrict__ small,
+__device__ __forceinline__ void scan_small(const float* __restrict__ table, int np, float R2, float sigma_per_len, const float4* __restrict__ small,
                                            V3<float> o, V3<float> dhat, float inv_a, float t_min, int self_pos, V3<float> self_n,
                                            uint16_t* cand, int cand_stride, float* t_best, int* p_best)
 {
-    const int n4 = np >> 2;
-    const float4* CX = reinterpret_cast<const float4*>(s_soa);
-    const float4* CY = CX + n4;
-    const float4* CZ = CY + n4;
-    const float4* KK = CZ + n4;
-    const FilterRay f = make_filter_ray(o, dhat);
     const int n_words = np >> 5;
     int pb = *p_best; float tb = *t_best;
     // the sphere the ray starts on is tested on its own, independently of the filter
     if (self_pos >= 0) candidate_self<float>(dhat, inv_a, t_min, self_n, small[self_pos].w, self_pos, &tb, &pb);
-
-    // software pipeline: the quad (4 spheres x 4 arrays, 4 LDS.128) for step q+1 is loaded while step q
-    // computes, so the ~30-cycle shared-memory latency hides behind 16 FFMA2 of the same warp
     if (n_words == 0) { *p_best = pb; *t_best = tb; return; }
-    float4 ncx = CX[0], ncy = CY[0], ncz = CZ[0], nkk = KK[0];
+
+    const FilterRay f = make_filter_ray(o, dhat, inv_a, R2, sigma_per_len);
+    const float4* rec = reinterpret_cast<const float4*>(table);
+    float4 ncx = rec[0], ncy = rec[1], ncz = rec[2], nkk = rec[3];
     for (int w0 = 0; w0 < n_words; w0 += RT_SEG_WORDS) {
         const int w1 = min(w0 + RT_SEG_WORDS, n_words);
         int nc = 0;
-        for (int w = w0; w < w1; ++w) {
-            const int q0 = w << 3;
-            const int q_next_word = (w + 1 < n_words) ? q0 + 8 : q0;     // the last word re-reads its first quad (unused)
-            const unsigned m = w < w_cull ? filter_word<true>(CX, CY, CZ, KK, q0, q_next_word, f, ncx, ncy, ncz, nkk)
-                                          : filter_word<false>(CX, CY, CZ, KK, q0, q_next_word, f, ncx, ncy, ncz, nkk);
-            unsigned c = ~m;                         // bit (31-k) set: sphere 32w+k passed the filter
+        for (int w = w0; w < w1; ++w, rec += 32) {
+            unsigned c = ~filter_word(rec, f, ncx, ncy, ncz, nkk);      // bit (31-k) set: sphere 32w+k passed the filter
             while (c) {
                 const int k = __clz(c);
                 c &= ~(0x80000000u >> k);
@@ -191,13 +201,13 @@ __device__ __forceinline__ void scan_small(const float* __restrict__ s_soa, int 
 // must call together.  self_code / self_n identify the sphere the ray starts on (RT_SELF_NONE for
 // camera rays).  Returns t in dhat units, the list index (or -1) and the winner's code.
 template <bool kSmem>
-__device__ __forceinline__ HitF closest_hit(const SceneDev& sc, const float* s_soa, V3<float> o, V3<float> dhat, float t_min,
+__device__ __forceinline__ HitF closest_hit(const SceneDev& sc, const float* table, V3<float> o, V3<float> dhat, float t_min,
                                             int self_code, V3<float> self_n, uint16_t* cand, int cand_stride)
 {
     const float inv_a = 1.0f / length_squared(dhat);
     float tb = __int_as_float(0x7f800000);   // f64::INFINITY at main.rs:44
     int pb = -1;
-    scan_small<kSmem>(s_soa, sc.np, sc.w_cull, sc.small, o, dhat, inv_a, t_min, self_code, self_n, cand, cand_stride, &tb, &pb);
+    scan_small<kSmem>(table, sc.np, sc.filter_R2, sc.filter_sigma, sc.small, o, dhat, inv_a, t_min, self_code, self_n, cand, cand_stride, &tb, &pb);
     HitF h; h.t = tb; h.idx = pb >= 0 ? sc.small_idx[pb] : -1; h.code = pb;
     if (sc.nb > 0) {
         const V3<double> od = mk<double>(o.x, o.y, o.z), dd = mk<double>(dhat.x, dhat.y, dhat.z);
@@ -235,12 +245,13 @@ __device__ __forceinline__ void closest_hit_f64(const SceneDev& sc, V3<double> o
     *t_out = tb; *idx_out = ib;
 }
 
-// cooperative copy of the filter SoA into shared memory (16-byte vector copies; np % 32 == 0)
-__device__ __forceinline__ void stage_scene(float* s_soa, const float* __restrict__ g_soa, int np)
+// cooperative copy of the filter table into shared memory (16-byte vector copies)
+__device__ __forceinline__ void stage_scene(float* s_table, const float* __restrict__ g_table, int np)
 {
-    const float4* src = reinterpret_cast<const float4*>(g_soa);
-    float4* dst = reinterpret_cast<float4*>(s_soa);
-    for (int i = threadIdx.x; i < np; i += blockDim.x) dst[i] = src[i];   // 4*np floats = np float4
+    const float4* src = reinterpret_cast<const float4*>(g_table);
+    float4* dst = reinterpret_cast<float4*>(s_table);
+    const int n4 = (int)(RT_TABLE_FLOATS(np) / 4);
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = src[i];
     __syncthreads();
 }
 

@@ -37,10 +37,10 @@ __global__ void __launch_bounds__(kThreads) hitlist_kernel(SceneDev sc, int64_t 
                                                            int32_t* hit, int32_t* index, double* t, double* p, double* normal, int32_t* front_face)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* s_soa = reinterpret_cast<float*>(smem_raw);
-    const float* soa = sc.soa;
+    float* s_table = reinterpret_cast<float*>(smem_raw);
+    const float* table = sc.table;
     uint16_t* cand_base;
-    if (kSmem) { stage_scene(s_soa, sc.soa, sc.np); soa = s_soa; cand_base = reinterpret_cast<uint16_t*>(s_soa + 4 * (size_t)sc.np); }
+    if (kSmem) { stage_scene(s_table, sc.table, sc.np); table = s_table; cand_base = reinterpret_cast<uint16_t*>(s_table + RT_TABLE_FLOATS(sc.np)); }
     else cand_base = reinterpret_cast<uint16_t*>(smem_raw);
     uint16_t* cand = cand_base + threadIdx.x;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(kThreads) hitlist_kernel(SceneDev sc, int64_t 
     const T tmin_n = (T)t_min * len;
     T th; int idx;
     if (sizeof(T) == 4) {
-        HitF h = closest_hit<kSmem>(sc, soa, mk<float>((float)o.x, (float)o.y, (float)o.z), mk<float>((float)dhat.x, (float)dhat.y, (float)dhat.z),
+        HitF h = closest_hit<kSmem>(sc, table, mk<float>((float)o.x, (float)o.y, (float)o.z), mk<float>((float)dhat.x, (float)dhat.y, (float)dhat.z),
                                     (float)tmin_n, RT_SELF_NONE, mk<float>(0, 1, 0), cand, kThreads);
         th = (T)h.t; idx = h.idx;
     } else {
@@ -141,10 +141,10 @@ __global__ void __launch_bounds__(kThreads) ray_color_kernel(SceneDev sc, int64_
                                                              double* color, unsigned long long* rays)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* s_soa = reinterpret_cast<float*>(smem_raw);
-    const float* soa = sc.soa;
+    float* s_table = reinterpret_cast<float*>(smem_raw);
+    const float* table = sc.table;
     uint16_t* cand_base;
-    if (kSmem) { stage_scene(s_soa, sc.soa, sc.np); soa = s_soa; cand_base = reinterpret_cast<uint16_t*>(s_soa + 4 * (size_t)sc.np); }
+    if (kSmem) { stage_scene(s_table, sc.table, sc.np); table = s_table; cand_base = reinterpret_cast<uint16_t*>(s_table + RT_TABLE_FLOATS(sc.np)); }
     else cand_base = reinterpret_cast<uint16_t*>(smem_raw);
     uint16_t* cand = cand_base + threadIdx.x;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(kThreads) ray_color_kernel(SceneDev sc, int64_
     while (__any_sync(RT_FULL, active)) {
         V3<T> rad = mk<T>(0, 0, 0);
         const bool was = active;
-        active = bounce_step<T, kSmem>(sc, soa, cand, kThreads, seed, (T)t_min, active, ps, &rad, &nr);
+        active = bounce_step<T, kSmem>(sc, table, cand, kThreads, seed, (T)t_min, active, ps, &rad, &nr);
         if (was && !active) result = rad;
     }
     if (i < n) { st3(color, i, result); if (rays) rays[i] = nr; }
