@@ -159,6 +159,70 @@ def test_hitlist_ragged_scene_sizes(ctx, oracle, n_spheres):
         assert t_err(got["t"][m], ref["t"][m], o[m], d[m], c[hi][m]).max() < 1e-5
 
 
+def test_hitlist_filter_line_point_far_and_degenerate_origins(ctx_final, oracle, final_scene):
+    """The f32 filter replaces the ray origin by the point where the ray's LINE enters the scene's bounding R-sphere
+    (rt_scene.cuh, make_filter_ray).  Exercise the geometry of that construction: origins 30 ... 2000 units away (|o| >> R),
+    the coordinate origin itself, origins outside the R-sphere looking away, and lines that miss the R-sphere altogether.
+    A filter that dropped a true hit would show up as a wrong / missing index on a ROBUST hit (chord well inside the sphere)."""
+    arrays = f32_scene(final_scene[0]); sc = oracle.Scene(**arrays)
+    ctx_final.upload_scene(**arrays)
+    rng = np.random.default_rng(23)
+    n = 40_000
+    k = rng.integers(1, sc.n, n)                                   # aim at (a point inside) sphere k
+    inside = rng.normal(size=(n, 3)); inside *= (rng.uniform(0, 0.6, (n, 1)) / np.linalg.norm(inside, axis=1, keepdims=True))
+    target = arrays["center"][k] + inside * np.abs(arrays["radius"][k])[:, None]
+    u = rng.normal(size=(n, 3)); u[:, 1] = np.abs(u[:, 1]) * 0.5 + 0.05; u /= np.linalg.norm(u, axis=1, keepdims=True)   # from above the ground
+    L = 10 ** rng.uniform(1.5, 3.3, (n, 1))
+    far_o = target + u * L; far_d = -u * rng.uniform(0.3, 3.0, (n, 1))
+    zero_o = np.zeros((2000, 3)); zero_d = rng.normal(size=(2000, 3))
+    away_o = far_o[:2000]; away_d = -far_d[:2000]
+    perp = np.cross(u[:2000], rng.normal(size=(2000, 3)))          # lines passing ~L away from the scene
+    o = f32(np.concatenate([far_o, zero_o, away_o, far_o[:2000]])); d = f32(np.concatenate([far_d, zero_d, away_d, perp]))
+    ref = oracle.world_hit_batch(sc, o, d)
+    got = ctx_final.hitlist_batch(o, d, 1e-4)
+    want = np.where(ref["hit"] == 1, ref["index"], -1)
+    hi = np.maximum(want, 0)
+    dist = np.linalg.norm(o - arrays["center"][hi], axis=1)
+    # robust: the chord is deep inside the sphere, by far more than f32 can misplace a line through an origin `dist` away
+    robust = (want >= 0) & not_grazing(arrays["center"][hi], arrays["radius"][hi], o, d, thr=0.2) & (dist * 1e-6 < 0.02 * np.abs(arrays["radius"][hi]))
+    assert robust[:n].mean() > 0.5
+    # the only excuse for a different winner is that the GPU's winner is itself a knife edge: a sphere in FRONT whose
+    # silhouette the line touches within what f32 can resolve from `dist` away (|disc|/a below ~4 r dist 1e-6)
+    gi = np.maximum(got["index"], 0)
+    cg, rg = arrays["center"][gi], arrays["radius"][gi]
+    oc = o - cg; a = (d * d).sum(1)
+    disc_g = ((oc * d).sum(1) ** 2 - a * ((oc * oc).sum(1) - rg * rg)) / a
+    knife = (got["index"] >= 0) & (np.abs(disc_g) < np.maximum(2e-3 * rg * rg, 4e-6 * np.abs(rg) * np.linalg.norm(oc, axis=1)))
+    lost = robust & (got["index"] != want) & ~knife
+    assert not lost.any(), f"{lost.sum()} robust hits lost or misplaced"
+    assert (got["index"] == want).mean() > 0.995
+    tail_w, tail_g = want[n + 2000:], got["index"][n + 2000:]          # looking away / passing far off: sky or the (f64) ground, never a small sphere
+    assert (tail_w <= 0).all() and (tail_w == -1).mean() > 0.4 and np.array_equal(tail_g, tail_w)
+
+
+def test_hitlist_scene_far_from_coordinate_origin(ctx, oracle):
+    """a scene centred 360 units from the coordinate origin: the bounding R-sphere is large, the filter's slack balloons
+    (more candidates), but every robust hit must still be found — the filter may only err towards keeping a sphere"""
+    rng = np.random.default_rng(5)
+    n_s = 300
+    off = np.array([300.0, 50.0, -200.0])
+    c = f32(off + rng.uniform(-8, 8, (n_s, 3))); r = f32(rng.uniform(0.1, 0.8, n_s))
+    sc = oracle.Scene(c, r, np.zeros(n_s, np.uint32), [0], [[1, 1, 1]], [0])
+    ctx.upload_scene(c, r, np.zeros(n_s, np.uint32), [0], [[1, 1, 1]], [0])
+    n = 20_000
+    k = rng.integers(0, n_s, n)
+    u = rng.normal(size=(n, 3)); u /= np.linalg.norm(u, axis=1, keepdims=True)
+    o = f32(c[k] + u * rng.uniform(2, 40, (n, 1)) + rng.normal(size=(n, 3)) * 0.3 * r[k][:, None]); d = f32(-u * rng.uniform(0.5, 2, (n, 1)))
+    ref = oracle.world_hit_batch(sc, o, d)
+    got = ctx.hitlist_batch(o, d, 1e-4)
+    want = np.where(ref["hit"] == 1, ref["index"], -1)
+    hi = np.maximum(want, 0)
+    robust = (want >= 0) & not_grazing(c[hi], r[hi], o, d, thr=0.2)            # coordinates ~360: one f32 ulp is 3e-5, r >= 0.1
+    assert robust.mean() > 0.4
+    assert np.array_equal(got["index"][robust], want[robust])
+    assert (got["index"] == want).mean() > 0.99
+
+
 def test_hitlist_many_candidates_per_ray(ctx, oracle):
     """a ray threading a long row of spheres overflows the per-lane candidate list (RT_CAND_CAP) — still exact"""
     n = 200
