@@ -96,6 +96,28 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1,
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+// The ten round keys of a seed, expanded once (on the host for the render kernel: they arrive as kernel parameters, i.e.
+// as constant-bank operands of the XORs, instead of 18 uniform-datapath additions per block).
+struct PhiloxKey { uint32_t k[20]; };
+__host__ __device__ __forceinline__ PhiloxKey philox_key(uint64_t seed)
+{
+    PhiloxKey key; uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) { key.k[2 * r] = k0; key.k[2 * r + 1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+    return key;
+}
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKey& key, uint32_t out[4])
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ key.k[2 * r];
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ key.k[2 * r + 1];
+        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
 // 24-bit uniform in [0,1): exactly representable in float and double, so the float renderer, the
 // double renderer and the CPU oracle consume identical random numbers.
 template <typename T> __host__ __device__ __forceinline__ T u01(uint32_t x) { return T(x >> 8) * T(1.0 / 16777216.0); }
@@ -105,6 +127,13 @@ template <typename T> __device__ __forceinline__ Uniform4<T> event_uniforms(uint
 {
     uint32_t o[4];
     philox4x32_10(pixel, sample, bounce, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), o);
+    Uniform4<T> u; u.u0 = u01<T>(o[0]); u.u1 = u01<T>(o[1]); u.u2 = u01<T>(o[2]); u.u3 = u01<T>(o[3]);
+    return u;
+}
+template <typename T> __device__ __forceinline__ Uniform4<T> event_uniforms(const PhiloxKey& key, uint32_t pixel, uint32_t sample, uint32_t bounce)
+{
+    uint32_t o[4];
+    philox4x32_10(pixel, sample, bounce, 0u, key, o);
     Uniform4<T> u; u.u0 = u01<T>(o[0]); u.u1 = u01<T>(o[1]); u.u2 = u01<T>(o[2]); u.u3 = u01<T>(o[3]);
     return u;
 }

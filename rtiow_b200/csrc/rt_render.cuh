@@ -19,7 +19,7 @@ template <typename T> struct RenderArgs {
     int32_t max_depth;
     T t_min;
     T inv_wm1, inv_hm1;            // 1/(width-1), 1/(height-1): the jitter denominators of main.rs:131-132
-    uint64_t seed;
+    PhiloxKey key;                 // Philox4x32-10 round keys of the sample seed
     // frame partition: this launch renders rows {y : (y / tile_rows) % world == rank}
     uint32_t rank, world, tile_rows, local_rows;
     uint32_t chunk_samples;        // samples per chunk (<= spp); chunks never straddle pixels
@@ -53,12 +53,13 @@ __device__ __forceinline__ uint32_t local_to_global_row(uint32_t lr, uint32_t ti
 }
 
 // One path in flight (one lane).  The ray is (o, dhat) with |dir| folded into tmin_n; self_* name the
-// sphere the ray starts on (rt_scene.cuh, candidate_self).
+// sphere the ray starts on (rt_scene.cuh, candidate_self).  The Philox event number of the path's next scatter is
+// max_depth - depth + 1 (event 0 is the camera ray), so no separate bounce counter is carried.
 template <typename T> struct PathState {
     V3<T> o, dhat, thr, self_n;
     T tmin_n;
     int self_code;
-    uint32_t pix_key, smp, bounce;
+    uint32_t pix_key, smp;
     int depth;
 };
 
@@ -73,19 +74,38 @@ template <typename T> __device__ __forceinline__ void start_ray(PathState<T>& ps
     ps.tmin_n = t_min * len;                        // t is measured in |dir| units (Appendix C.3)
 }
 
-// The part of ray_color (main.rs:38-57) that follows world.hit: the miss / scatter / absorb branches for one lane.
-// (t_hit, idx, code) is the closest hit of the lane's ray (idx < 0: none).  Returns the lane's new `active`; when the path
-// ends, *radiance receives its value (throughput x sky, or black).
-template <typename T>
-__device__ __forceinline__ bool shade_step(const SceneDev& sc, uint64_t seed, T t_min, bool active, PathState<T>& ps, T t_hit, int idx, int code,
-                                           V3<T>* radiance, uint32_t* n_rays)
+template <typename T> __device__ __forceinline__ void init_path(PathState<T>& ps)
 {
-    if (!active) return false;
-    ++*n_rays;
-    if (idx < 0) {                                                            // miss: sky (main.rs:54-56)
-        *radiance = ps.thr * sky<T, sizeof(T) == 4>(ps.dhat);
-        return false;
+    ps.o = mk<T>(0, 0, 0); ps.dhat = mk<T>(0, 1, 0); ps.thr = mk<T>(0, 0, 0); ps.self_n = mk<T>(0, 1, 0);
+    ps.tmin_n = T(0); ps.self_code = RT_SELF_NONE; ps.pix_key = 0; ps.smp = 0; ps.depth = 0;
+}
+
+// world.hit(r, t_min, INFINITY) (main.rs:44) for every lane of the warp (all 32 must call: the scan's warp-level
+// operations need them); lanes without a ray get a result they ignore.
+template <typename T, bool kSmem>
+__device__ __forceinline__ void world_hit(const SceneDev& sc, const float* table, uint16_t* cand, int cand_stride, const PathState<T>& ps,
+                                          T* t_hit, int* idx, int* code)
+{
+    if (sizeof(T) == 4) {
+        const HitF h = closest_hit<kSmem>(sc, table, mk<float>((float)ps.o.x, (float)ps.o.y, (float)ps.o.z),
+                                          mk<float>((float)ps.dhat.x, (float)ps.dhat.y, (float)ps.dhat.z), (float)ps.tmin_n, ps.self_code,
+                                          mk<float>((float)ps.self_n.x, (float)ps.self_n.y, (float)ps.self_n.z), cand, cand_stride);
+        *t_hit = (T)h.t; *idx = h.idx; *code = h.code;
+    } else {
+        double td;
+        closest_hit_f64(sc, mk<double>(ps.o.x, ps.o.y, ps.o.z), mk<double>(ps.dhat.x, ps.dhat.y, ps.dhat.z), (double)ps.tmin_n, ps.self_code,
+                        mk<double>(ps.self_n.x, ps.self_n.y, ps.self_n.z), &td, idx);
+        *t_hit = (T)td; *code = *idx;
     }
+}
+
+// The hit branch of ray_color (main.rs:46-52) for one lane: HitRecord::new at p (sphere.rs:36-39), Scatter::scatter
+// (main.rs:47) with the event's random numbers, then the scattered ray.  (sa, sb, z) is the event's uniform unit vector
+// (materials.rs:23 adds it to the normal; materials.rs:53 scales it into the ball by cbrt(u2)); u0 is xi for glass
+// (materials.rs:96).  Returns false when the path ends here in black (absorbed: main.rs:51, or depth exhausted: main.rs:40-42).
+template <typename T>
+__device__ __forceinline__ bool scatter_at_hit(const SceneDev& sc, T t_min, PathState<T>& ps, V3<T> p, int idx, int code, T sa, T sb, T z, T u0, T u2)
+{
     V3<T> cen; T rad; V3<T> albedo; T param;
     if (sizeof(T) == 4) {
         const float4 s = sc.sph[idx], m = sc.mat[idx];
@@ -95,23 +115,16 @@ __device__ __forceinline__ bool shade_step(const SceneDev& sc, uint64_t seed, T 
         cen = mk<T>(s.x, s.y, s.z); rad = s.w; albedo = mk<T>(m.x, m.y, m.z); param = m.w;
     }
     const int kind = sc.kind[idx];
-    const V3<T> p = ps.o + ps.dhat * t_hit;                                   // ray.rs:15-17
     V3<T> n; bool ff; hit_record(p, cen, rad, ps.dhat, &n, &ff);             // sphere.rs:36-39
-    ++ps.bounce;
-    const Uniform4<T> u = event_uniforms<T>(seed, ps.pix_key, ps.smp, ps.bounce);
-    // one unit vector for both diffuse (materials.rs:23) and metal (materials.rs:53: scaled into the ball); xi for glass (materials.rs:96)
-    V3<T> sample = mk<T>(u.u0, 0, 0);
+    V3<T> sample = mk<T>(u0, 0, 0);
     if (kind != MAT_DIELECTRIC) {
-        sample = direct_unit_vector(u.u0, u.u1);
-        if (kind == MAT_METAL) sample = sample * cbrt_t(u.u2);
+        sample = mk<T>(sa, sb, z);
+        if (kind == MAT_METAL) sample = sample * cbrt_t(u2);
     }
     V3<T> att, nd;
     const bool some = scatter<T, sizeof(T) == 4>(kind, albedo, param, ps.dhat, n, ff, sample, &att, &nd);   // main.rs:47
     --ps.depth;
-    if (!some || ps.depth <= 0) {                                             // main.rs:51 / main.rs:40-42: black
-        *radiance = mk<T>(0, 0, 0);
-        return false;
-    }
+    if (!some || ps.depth <= 0) return false;
     ps.thr = ps.thr * att;                                                    // main.rs:49 as a running product
     start_ray(ps, p, nd, t_min);
     ps.self_code = code;
@@ -121,28 +134,40 @@ __device__ __forceinline__ bool shade_step(const SceneDev& sc, uint64_t seed, T 
     return true;
 }
 
-// One iteration of ray_color (main.rs:38-57) for every lane of the warp: world.hit, then shade_step.  Lanes with
-// active == false still take part in the scan (its warp-level operations need all 32) but ignore the result.
-template <typename T, bool kSmem>
-__device__ __forceinline__ bool bounce_step(const SceneDev& sc, const float* table, uint16_t* cand, int cand_stride, uint64_t seed, T t_min,
-                                            bool active, PathState<T>& ps, V3<T>* radiance, uint32_t* n_rays)
+// The event's shared sampler: one sincospi and one sqrt serve the lens disk of a camera ray (camera.rs:48: radius
+// sqrt(u2), angle 2 pi u3 — direct_disk) and the unit vector of a scatter (z = 1 - 2 u0, angle 2 pi u1 — direct_unit_vector).
+template <typename T>
+__device__ __forceinline__ void event_sample(bool camera, const Uniform4<T>& u, T* sa, T* sb, T* z)
 {
-    T t_hit; int idx, code;
-    if (sizeof(T) == 4) {                                                     // world.hit(r, t_min, INFINITY), main.rs:44
-        const HitF h = closest_hit<kSmem>(sc, table, mk<float>((float)ps.o.x, (float)ps.o.y, (float)ps.o.z),
-                                          mk<float>((float)ps.dhat.x, (float)ps.dhat.y, (float)ps.dhat.z), (float)ps.tmin_n, ps.self_code,
-                                          mk<float>((float)ps.self_n.x, (float)ps.self_n.y, (float)ps.self_n.z), cand, cand_stride);
-        t_hit = (T)h.t; idx = h.idx; code = h.code;
-    } else {
-        double td;
-        closest_hit_f64(sc, mk<double>(ps.o.x, ps.o.y, ps.o.z), mk<double>(ps.dhat.x, ps.dhat.y, ps.dhat.z), (double)ps.tmin_n, ps.self_code,
-                        mk<double>(ps.self_n.x, ps.self_n.y, ps.self_n.z), &td, &idx);
-        t_hit = (T)td; code = idx;
-    }
-    return shade_step<T>(sc, seed, t_min, active, ps, t_hit, idx, code, radiance, n_rays);
+    *z = T(1) - T(2) * u.u0;
+    T sn, cs; sincospi_t(T(2) * (camera ? u.u3 : u.u1), &sn, &cs);
+    const T rr = sqrt_t(camera ? u.u2 : max_t(T(0), T(1) - *z * *z));
+    *sa = rr * cs; *sb = rr * sn;
 }
 
-// ---- the pixel/sample loop's bookkeeping (main.rs:122-135), shared by the render kernels ------------------------------
+// One iteration of ray_color (main.rs:38-57) for every lane of the warp, on explicit rays (the unit-level entry point
+// rtiow_ray_color_batch): world.hit, then miss -> sky / hit -> scatter.  Returns the lane's new `active`; when the path
+// ends, *radiance receives its value (throughput x sky, or black).  The render kernel below runs the same pieces in a
+// different order (scatter of the previous hit and camera rays share one Philox block + sampler per iteration).
+template <typename T, bool kSmem>
+__device__ __forceinline__ bool bounce_step(const SceneDev& sc, const float* table, uint16_t* cand, int cand_stride, const PhiloxKey& key, int max_depth,
+                                            T t_min, bool active, PathState<T>& ps, V3<T>* radiance)
+{
+    T t_hit; int idx, code;
+    world_hit<T, kSmem>(sc, table, cand, cand_stride, ps, &t_hit, &idx, &code);
+    if (!active) return false;
+    if (idx < 0) {                                                            // miss: sky (main.rs:54-56)
+        *radiance = ps.thr * sky<T, sizeof(T) == 4>(ps.dhat);
+        return false;
+    }
+    const V3<T> p = ps.o + ps.dhat * t_hit;                                   // ray.rs:15-17
+    const Uniform4<T> u = event_uniforms<T>(key, ps.pix_key, ps.smp, (uint32_t)(max_depth - ps.depth) + 1u);
+    T sa, sb, z; event_sample(false, u, &sa, &sb, &z);
+    if (!scatter_at_hit(sc, t_min, ps, p, idx, code, sa, sb, z, u.u0, u.u2)) { *radiance = mk<T>(0, 0, 0); return false; }
+    return true;
+}
+
+// ---- the pixel/sample loop's bookkeeping (main.rs:122-135) ---------------------------------------------------------
 // warp-uniform cursor over the work: chunks (<= 256 samples of ONE pixel) fetched from a global atomic counter
 struct WorkCursor {
     uint32_t cs = 0, ce = 0, c_lp = 0, c_x = 0, c_y = 0;
@@ -150,23 +175,19 @@ struct WorkCursor {
     bool exhausted = false;
 };
 
-template <typename T> __device__ __forceinline__ void init_path(PathState<T>& ps)
-{
-    ps.o = mk<T>(0, 0, 0); ps.dhat = mk<T>(0, 1, 0); ps.thr = mk<T>(0, 0, 0); ps.self_n = mk<T>(0, 1, 0);
-    ps.tmin_n = T(0); ps.self_code = RT_SELF_NONE; ps.pix_key = 0; ps.smp = 0; ps.bounce = 0; ps.depth = 0;
-}
-
-// regeneration: every lane whose path slot is idle starts the next (pixel, sample) of the warp's chunk (main.rs:130-134)
+// Every lane whose slot is free (`busy` false) takes the next (pixel, sample) of the warp's chunk (main.rs:130).  Returns
+// true for the lanes that received one; their pixel column / bottom-up row come back in *px, *pj.
 template <typename T>
-__device__ __forceinline__ void regenerate(const RenderArgs<T>& a, WorkCursor& wc, unsigned lane, unsigned lt_mask, bool& active, PathState<T>& ps,
-                                           uint32_t& acc_lp)
+__device__ __forceinline__ bool assign_work(const RenderArgs<T>& a, WorkCursor& wc, unsigned lt_mask, bool busy, PathState<T>& ps, uint32_t& acc_lp,
+                                            uint32_t* px, uint32_t* pj)
 {
-    unsigned need = __ballot_sync(RT_FULL, !active);
+    bool fresh = false;
+    unsigned need = __ballot_sync(RT_FULL, !busy);
     while (need && !wc.exhausted) {
         if (wc.cs == wc.ce) {
             if (wc.cc == wc.cce) {
                 unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(a.work_counter, (unsigned long long)a.chunks_per_fetch);
+                if (lt_mask == 0u) base = atomicAdd(a.work_counter, (unsigned long long)a.chunks_per_fetch);      // lane 0
                 wc.cc = __shfl_sync(RT_FULL, base, 0);
                 wc.cce = wc.cc + a.chunks_per_fetch; if (wc.cce > a.n_chunks) wc.cce = a.n_chunks;
                 if (wc.cc >= a.n_chunks) { wc.exhausted = true; break; }
@@ -181,24 +202,18 @@ __device__ __forceinline__ void regenerate(const RenderArgs<T>& a, WorkCursor& w
         }
         const uint32_t avail = wc.ce - wc.cs;
         const uint32_t r = __popc(need & lt_mask);
-        if (!active && r < avail) {
+        if (!busy && !fresh && r < avail) {
+            fresh = true;
             acc_lp = wc.c_lp;
             ps.smp = wc.cs + r;
-            const uint32_t j = a.height - 1u - wc.c_y;              // j = 0 is the bottom row (main.rs:132,141-145)
-            ps.pix_key = j * a.width + wc.c_x;
-            const Uniform4<T> u = event_uniforms<T>(a.seed, ps.pix_key, ps.smp, 0u);
-            const T su = (T(wc.c_x) + u.u0) * a.inv_wm1;             // main.rs:131
-            const T sv = (T(j) + u.u1) * a.inv_hm1;                  // main.rs:132
-            T dx, dy; direct_disk(u.u2, u.u3, &dx, &dy);            // camera.rs:48
-            V3<T> ro, rd; get_ray(a.cam, su, sv, dx, dy, &ro, &rd); // main.rs:134
-            start_ray(ps, ro, rd, a.t_min);
-            ps.thr = mk<T>(1, 1, 1); ps.self_code = RT_SELF_NONE;
-            ps.depth = a.max_depth; ps.bounce = 0;
-            active = ps.depth > 0;                                   // main.rs:40-42
+            *px = wc.c_x;
+            *pj = a.height - 1u - wc.c_y;                            // j = 0 is the bottom row (main.rs:132,141-145)
+            ps.pix_key = *pj * a.width + wc.c_x;
         }
         wc.cs += min((uint32_t)__popc(need), avail);
-        need = __ballot_sync(RT_FULL, !active);
+        need = __ballot_sync(RT_FULL, !busy && !fresh);
     }
+    return fresh;
 }
 
 // pixel_color += ray_color (main.rs:135): 32.32 fixed-point RED.ADD.U64 straight into the frame's accumulators
@@ -214,43 +229,59 @@ __device__ __forceinline__ void accumulate(const RenderArgs<T>& a, uint32_t acc_
     }
 }
 
+// The render kernel.  Per iteration of a warp:
+//   1. lanes without a path take the next (pixel, sample);
+//   2. ONE Philox block + ONE sincospi/sqrt per lane serve whatever event the lane is at — the camera ray of a fresh
+//      sample (main.rs:131-134) or the scatter at the hit found by the previous iteration (main.rs:47) — so the expensive
+//      common part runs once, converged, instead of once per divergent branch;
+//   3. the scan (world.hit) for all 32 lanes;
+//   4. miss -> throughput x sky is added to the pixel and the lane is free again; hit -> the lane keeps the hit for step 2.
 template <typename T, bool kSmem, int kThreads, int kMinCtas>
 __global__ void __launch_bounds__(kThreads, kMinCtas) render_kernel(const RenderArgs<T> a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* s_table = reinterpret_cast<float*>(smem_raw);
-    const int np = a.scene.np;
-    const float* table = a.scene.table;
-    uint16_t* cand_base;
-    if (kSmem) {
-        stage_scene(s_table, a.scene.table, np);
-        table = s_table;
-        cand_base = reinterpret_cast<uint16_t*>(s_table + RT_TABLE_FLOATS(np));
-    } else {
-        cand_base = reinterpret_cast<uint16_t*>(smem_raw);
-    }
-    uint16_t* cand = cand_base + threadIdx.x;          // slot k of this lane at cand[k * kThreads]
+    uint16_t* cand;
+    const float* table = setup_scan_smem<kSmem>(smem_raw, a.scene, kThreads, &cand);
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
 
-    // ---- per-lane path state, warp-uniform work cursor ----------------------------------------------
-    bool active = false;
     PathState<T> ps; init_path(ps);
     uint32_t acc_lp = 0;                                // local pixel of the path in flight
-    uint32_t n_rays = 0;
+    bool pending = false;                               // the lane's ray hit sphere hit_idx at ps.o: scatter to be evaluated
+    int hit_idx = -1, hit_code = RT_SELF_NONE;
+    uint32_t n_rays_w = 0;                              // warp-uniform: rays traced by this warp
     WorkCursor wc;
 
     for (;;) {
-        regenerate(a, wc, lane, lt_mask, active, ps, acc_lp);
-        if (!__any_sync(RT_FULL, active)) break;
-        V3<T> rad = mk<T>(0, 0, 0);
-        const bool was = active;
-        active = bounce_step<T, kSmem>(a.scene, table, cand, kThreads, a.seed, a.t_min, active, ps, &rad, &n_rays);
-        if (was && !active) accumulate(a, acc_lp, rad);
+        uint32_t px = 0, pj = 0;
+        const bool fresh = assign_work(a, wc, lt_mask, pending, ps, acc_lp, &px, &pj);
+        if (!__any_sync(RT_FULL, fresh || pending)) break;
+
+        const Uniform4<T> u = event_uniforms<T>(a.key, ps.pix_key, ps.smp, fresh ? 0u : (uint32_t)(a.max_depth - ps.depth) + 1u);
+        T sa, sb, z; event_sample(fresh, u, &sa, &sb, &z);
+        bool active = false;                            // the lane has a ray for this iteration's scan
+        if (fresh) {
+            const T su = (T(px) + u.u0) * a.inv_wm1;                 // main.rs:131
+            const T sv = (T(pj) + u.u1) * a.inv_hm1;                 // main.rs:132
+            V3<T> ro, rd; get_ray(a.cam, su, sv, sa, sb, &ro, &rd);  // main.rs:134
+            start_ray(ps, ro, rd, a.t_min);
+            ps.thr = mk<T>(1, 1, 1); ps.self_code = RT_SELF_NONE;
+            ps.depth = a.max_depth;
+            active = ps.depth > 0;                                   // main.rs:40-42
+        } else if (pending) {
+            active = scatter_at_hit(a.scene, a.t_min, ps, ps.o, hit_idx, hit_code, sa, sb, z, u.u0, u.u2);
+        }
+        pending = false;
+
+        n_rays_w += __popc(__ballot_sync(RT_FULL, active));          // world.hit call count (main.rs:44)
+        T t_hit; int idx, code;
+        world_hit<T, kSmem>(a.scene, table, cand, kThreads, ps, &t_hit, &idx, &code);
+        if (active) {
+            if (idx < 0) accumulate(a, acc_lp, ps.thr * sky<T, sizeof(T) == 4>(ps.dhat));     // miss: sky (main.rs:54-56)
+            else { ps.o = ps.o + ps.dhat * t_hit; hit_idx = idx; hit_code = code; pending = true; }   // ray.rs:15-17
+        }
     }
-    // rays traced by this warp -> one atomic (world.hit call count, main.rs:44)
-    uint32_t wr = __reduce_add_sync(RT_FULL, n_rays);
-    if (lane == 0) atomicAdd(a.ray_counter, (unsigned long long)wr);
+    if (lane == 0) atomicAdd(a.ray_counter, (unsigned long long)n_rays_w);
 }
 
 // Color::to_rgba (vec3.rs:404-420) + the row flip (main.rs:141-145): fixed-point sums -> top-down

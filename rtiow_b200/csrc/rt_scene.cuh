@@ -245,14 +245,21 @@ __device__ __forceinline__ void closest_hit_f64(const SceneDev& sc, V3<double> o
     *t_out = tb; *idx_out = ib;
 }
 
-// cooperative copy of the filter table into shared memory (16-byte vector copies)
-__device__ __forceinline__ void stage_scene(float* s_table, const float* __restrict__ g_table, int np)
+// Dynamic shared memory of every scanning kernel: [candidate lists: threads x RT_CAND_CAP uint16][filter table].
+// The lists come first so that a lane's slot address does not depend on the scene size.  Returns the table to scan
+// (the staged copy, or the global one when kSmem is false) and the lane's first list slot (slot k at cand[k * threads]).
+#define RT_CAND_BYTES(threads) ((size_t)(threads) * RT_CAND_CAP * sizeof(uint16_t))
+template <bool kSmem>
+__device__ __forceinline__ const float* setup_scan_smem(unsigned char* smem_raw, const SceneDev& sc, int threads, uint16_t** cand)
 {
-    const float4* src = reinterpret_cast<const float4*>(g_table);
-    float4* dst = reinterpret_cast<float4*>(s_table);
-    const int n4 = (int)(RT_TABLE_FLOATS(np) / 4);
-    for (int i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = src[i];
+    *cand = reinterpret_cast<uint16_t*>(smem_raw) + threadIdx.x;
+    if (!kSmem) return sc.table;
+    float4* dst = reinterpret_cast<float4*>(smem_raw + RT_CAND_BYTES(threads));
+    const float4* src = reinterpret_cast<const float4*>(sc.table);
+    const int n4 = (int)(RT_TABLE_FLOATS(sc.np) / 4);
+    for (int i = threadIdx.x; i < n4; i += threads) dst[i] = src[i];          // cooperative 16-byte copies
     __syncthreads();
+    return reinterpret_cast<const float*>(dst);
 }
 
 }  // namespace rt

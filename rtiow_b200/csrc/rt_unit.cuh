@@ -37,12 +37,8 @@ __global__ void __launch_bounds__(kThreads) hitlist_kernel(SceneDev sc, int64_t 
                                                            int32_t* hit, int32_t* index, double* t, double* p, double* normal, int32_t* front_face)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* s_table = reinterpret_cast<float*>(smem_raw);
-    const float* table = sc.table;
-    uint16_t* cand_base;
-    if (kSmem) { stage_scene(s_table, sc.table, sc.np); table = s_table; cand_base = reinterpret_cast<uint16_t*>(s_table + RT_TABLE_FLOATS(sc.np)); }
-    else cand_base = reinterpret_cast<uint16_t*>(smem_raw);
-    uint16_t* cand = cand_base + threadIdx.x;
+    uint16_t* cand;
+    const float* table = setup_scan_smem<kSmem>(smem_raw, sc, kThreads, &cand);
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < n;
     V3<T> o = mk<T>(0, 0, 0), d = mk<T>(0, 1, 0);
@@ -141,24 +137,21 @@ __global__ void __launch_bounds__(kThreads) ray_color_kernel(SceneDev sc, int64_
                                                              double* color, unsigned long long* rays)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* s_table = reinterpret_cast<float*>(smem_raw);
-    const float* table = sc.table;
-    uint16_t* cand_base;
-    if (kSmem) { stage_scene(s_table, sc.table, sc.np); table = s_table; cand_base = reinterpret_cast<uint16_t*>(s_table + RT_TABLE_FLOATS(sc.np)); }
-    else cand_base = reinterpret_cast<uint16_t*>(smem_raw);
-    uint16_t* cand = cand_base + threadIdx.x;
+    uint16_t* cand;
+    const float* table = setup_scan_smem<kSmem>(smem_raw, sc, kThreads, &cand);
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool active = i < n && max_depth > 0;
-    PathState<T> ps;
-    ps.o = mk<T>(0, 0, 0); ps.dhat = mk<T>(0, 1, 0); ps.thr = mk<T>(1, 1, 1); ps.self_n = mk<T>(0, 1, 0);
-    ps.tmin_n = T(0); ps.self_code = RT_SELF_NONE; ps.pix_key = 0; ps.smp = 0; ps.bounce = 0; ps.depth = max_depth;
+    PathState<T> ps; init_path(ps);
+    ps.thr = mk<T>(1, 1, 1); ps.depth = max_depth;
+    const PhiloxKey key = philox_key(seed);
     V3<T> result = mk<T>(0, 0, 0);
     uint32_t nr = 0;
     if (i < n) { start_ray(ps, ld3<T>(orig, i), ld3<T>(dir, i), (T)t_min); ps.pix_key = pixel[i]; ps.smp = sample[i]; }
     while (__any_sync(RT_FULL, active)) {
         V3<T> rad = mk<T>(0, 0, 0);
         const bool was = active;
-        active = bounce_step<T, kSmem>(sc, table, cand, kThreads, seed, (T)t_min, active, ps, &rad, &nr);
+        if (active) ++nr;                                                     // world.hit call count (main.rs:44)
+        active = bounce_step<T, kSmem>(sc, table, cand, kThreads, key, max_depth, (T)t_min, active, ps, &rad);
         if (was && !active) result = rad;
     }
     if (i < n) { st3(color, i, result); if (rays) rays[i] = nr; }
