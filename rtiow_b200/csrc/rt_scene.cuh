@@ -128,6 +128,8 @@ __device__ __forceinline__ FilterRay make_filter_ray(V3<float> o, V3<float> dhat
     const V3<float> p = f - dhat * s;                       // where the line enters the R-sphere (or its foot point)
     FilterRay r;
     r.M2PX = -2.0f * p.x; r.M2PY = -2.0f * p.y; r.M2PZ = -2.0f * p.z;
+    // opaque to the compiler: otherwise it keeps p and re-multiplies by -2 in every 32-sphere word (3 FMUL per word)
+    asm volatile("" : "+f"(r.M2PX), "+f"(r.M2PY), "+f"(r.M2PZ));
     r.DX = dhat.x; r.DY = dhat.y; r.DZ = dhat.z;
     r.NPD = -dot(p, dhat);
     return r;
