@@ -101,7 +101,7 @@ __device__ __forceinline__ void candidate_self(V3<T> dhat, T inv_a, T t_min, V3<
 //   RT_FILTER_SLACK (|c|^2 + r^2 + R^2) and p is placed slightly outside the R-sphere (|p|^2 = R^2 + sigma, sigma covering
 //   the f32 error of the foot point of a distant origin), so disc' >= 0 is a conservative superset of
 //   "discriminant >= 0" (sphere.rs:24-25).  Every survivor goes through the well-conditioned sphere_roots.
-//   A line that misses the R-sphere keeps its foot point (|p| > R: C only gets smaller, still conservative).
+//   A line that misses the R-sphere can hit no small sphere; its filter ray is zeroed so that nothing passes.
 //
 //   Candidates (a few per ray): positions appended to a per-lane list in shared memory, then the whole warp drains its
 //   lists in lock-step through candidate<float>.
@@ -124,14 +124,20 @@ __device__ __forceinline__ FilterRay make_filter_ray(V3<float> o, V3<float> dhat
     // |p|^2 = R^2 + sigma, sigma = 16 u r_max |o|_1: the foot point of a far origin is only known to ~4 u |o|
     const float sigma = sigma_per_len * (fabsf(o.x) + fabsf(o.y) + fabsf(o.z));
     const float h2 = (R2 + sigma) - ff;
-    const float s = h2 > 0.0f ? sqrtf(h2 * inv_a) : 0.0f;
-    const V3<float> p = f - dhat * s;                       // where the line enters the R-sphere (or its foot point)
+    const bool inside = h2 > 0.0f;                          // the line enters the R-sphere
+    const float s = inside ? sqrtf(h2 * inv_a) : 0.0f;
+    const V3<float> p = f - dhat * s;                       // where the line enters the R-sphere
     FilterRay r;
-    r.M2PX = -2.0f * p.x; r.M2PY = -2.0f * p.y; r.M2PZ = -2.0f * p.z;
+    // A line that misses the R-sphere (an origin far out on the ground, heading for the sky) can hit no small sphere:
+    // with p = 0 the filter computes (c.d)^2 - K <= |c|^2 - (|c|^2 - r^2 + R^2) < 0 for every sphere, as R >= |c| + |r|.
+    // (Keeping the foot point instead would stay conservative, but |p|^2 - R^2 would act as slack and let through every
+    // sphere within that distance of the line — hundreds of false candidates per such ray.)
+    const float live = inside ? 1.0f : 0.0f;
+    r.M2PX = -2.0f * live * p.x; r.M2PY = -2.0f * live * p.y; r.M2PZ = -2.0f * live * p.z;
     // opaque to the compiler: otherwise it keeps p and re-multiplies by -2 in every 32-sphere word (3 FMUL per word)
     asm volatile("" : "+f"(r.M2PX), "+f"(r.M2PY), "+f"(r.M2PZ));
     r.DX = dhat.x; r.DY = dhat.y; r.DZ = dhat.z;
-    r.NPD = -dot(p, dhat);
+    r.NPD = -live * dot(p, dhat);
     return r;
 }
 
