@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RTIOW_ABI_VERSION 1
+#define RTIOW_ABI_VERSION 2
 
 typedef enum {
     RTIOW_OK = 0,
@@ -33,7 +33,8 @@ typedef enum {
     RTIOW_ERR_CUDA = -3,
     RTIOW_ERR_NCCL = -4,
     RTIOW_ERR_NO_DEVICE = -5,
-    RTIOW_ERR_NOMEM = -6
+    RTIOW_ERR_NOMEM = -6,
+    RTIOW_ERR_CANCELLED = -7      /* rtiow_render_progressive: the callback asked to stop; out_rgba holds the frame so far */
 } rtiow_status;
 
 /* materials.rs:9-11 (Lambertian), 34-37 (Metal), 64-66 (Dialectric) */
@@ -119,6 +120,15 @@ void rtiow_params_default(rtiow_params* p);
 /* THE drop-in call: replaces main.rs:122-145.  Writes 4*width*height bytes, top-down RGBA8 — the
  * buffer handed to ImageBuffer::from_vec at main.rs:147 — into caller-owned HOST memory. */
 int rtiow_render(rtiow_ctx* ctx, const rtiow_camera* cam, const rtiow_params* p, uint8_t* out_rgba, rtiow_stats* stats);
+
+/* The reference shows progress per row (indicatif bar, main.rs:120,124) and the finished frame in a piston window
+ * (main.rs:151-171).  The GPU equivalent: the spp samples are rendered in n_passes slices (clamped to spp); after each slice
+ * on_pass(user, pass [1-based], n_passes, spp_done, rgba) receives the frame so far — out_rgba, top-down RGBA8, quantised
+ * with the samples done so far (vec3.rs:404-420).  A non-zero return stops the render (RTIOW_ERR_CANCELLED; out_rgba keeps
+ * the last frame).  on_pass may be NULL.  The final frame is bit-identical to rtiow_render's; stats are summed over passes. */
+typedef int (*rtiow_progress_fn)(void* user, uint32_t pass, uint32_t n_passes, uint32_t spp_done, const uint8_t* rgba);
+int rtiow_render_progressive(rtiow_ctx* ctx, const rtiow_camera* cam, const rtiow_params* p, uint32_t n_passes,
+                             rtiow_progress_fn on_pass, void* user, uint8_t* out_rgba, rtiow_stats* stats);
 
 /* --- one-process-per-GPU pieces (rank r of world G renders rows {y : (y / tile_rows) % G == r}) ---- */
 /* bytes of one rank's tile buffer (equal on every rank; padded when the tile count does not divide) */

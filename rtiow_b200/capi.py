@@ -13,18 +13,20 @@ import numpy as np
 
 from . import build as _build
 
-OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_NCCL, ERR_NO_DEVICE, ERR_NOMEM = 0, -1, -2, -3, -4, -5, -6
+OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_NCCL, ERR_NO_DEVICE, ERR_NOMEM, ERR_CANCELLED = 0, -1, -2, -3, -4, -5, -6, -7
 MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC = 0, 1, 2
 F32, F64 = 0, 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _STATUS = {OK: "OK", ERR_INVALID_ARG: "INVALID_ARG", ERR_UNSUPPORTED: "UNSUPPORTED", ERR_CUDA: "CUDA", ERR_NCCL: "NCCL",
-           ERR_NO_DEVICE: "NO_DEVICE", ERR_NOMEM: "NOMEM"}
+           ERR_NO_DEVICE: "NO_DEVICE", ERR_NOMEM: "NOMEM", ERR_CANCELLED: "CANCELLED"}
+# rtiow_progress_fn: int (*)(void* user, uint32_t pass, uint32_t n_passes, uint32_t spp_done, const uint8_t* rgba)
+PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p)
 
 # every symbol include/rtiow_cuda.h declares (tests check the .so exports exactly these)
 SYMBOLS = [
     "rtiow_abi_version", "rtiow_last_error", "rtiow_device_count", "rtiow_ctx_create", "rtiow_ctx_create_on_device",
-    "rtiow_ctx_destroy", "rtiow_scene_upload", "rtiow_camera_new", "rtiow_params_default", "rtiow_render",
+    "rtiow_ctx_destroy", "rtiow_scene_upload", "rtiow_camera_new", "rtiow_params_default", "rtiow_render", "rtiow_render_progressive",
     "rtiow_tile_buffer_bytes", "rtiow_render_tiles_device", "rtiow_deinterleave_device", "rtiow_sphere_hit_batch",
     "rtiow_hitlist_batch", "rtiow_scatter_batch", "rtiow_get_ray_batch", "rtiow_to_rgba_batch", "rtiow_reflect_batch",
     "rtiow_refract_batch", "rtiow_ray_color_batch", "rtiow_sampler_batch", "rtiow_fp32_peak_probe", "rtiow_flush_l2",
@@ -105,6 +107,7 @@ def _declare(L):
         "rtiow_camera_new": (C.c_int, [P, P, P, d, d, d, d, C.POINTER(Camera)]),
         "rtiow_params_default": (None, [C.POINTER(Params)]),
         "rtiow_render": (C.c_int, [P, C.POINTER(Camera), C.POINTER(Params), P, C.POINTER(Stats)]),
+        "rtiow_render_progressive": (C.c_int, [P, C.POINTER(Camera), C.POINTER(Params), C.c_uint32, PROGRESS_FN, P, P, C.POINTER(Stats)]),
         "rtiow_tile_buffer_bytes": (C.c_int, [C.POINTER(Params), C.c_int, C.POINTER(C.c_size_t)]),
         "rtiow_render_tiles_device": (C.c_int, [P, C.POINTER(Camera), C.POINTER(Params), C.c_int, C.c_int, P, P, C.POINTER(Stats)]),
         "rtiow_deinterleave_device": (C.c_int, [P, P, C.POINTER(Params), C.c_int, P, P]),
@@ -229,6 +232,22 @@ class Context:
         assert out.dtype == np.uint8 and out.size == params.height * params.width * 4 and out.flags.c_contiguous
         st = Stats()
         _check(lib().rtiow_render(self._h, C.byref(cam), C.byref(params), _p(out), C.byref(st)))
+        return out, st.as_dict()
+
+    def render_progressive(self, cam: Camera, params: Params, n_passes: int, on_pass=None, out: np.ndarray | None = None):
+        """rtiow_render_progressive: the spp samples in n_passes slices; on_pass(pass_1based, n_passes, spp_done, rgba[H,W,4] view)
+        is called after each (return True to cancel -> RtiowError ERR_CANCELLED).  -> (final rgba, stats summed over passes)."""
+        if out is None:
+            out = np.empty((params.height, params.width, 4), np.uint8)
+        assert out.dtype == np.uint8 and out.size == params.height * params.width * 4 and out.flags.c_contiguous
+        view = out.reshape(params.height, params.width, 4)
+
+        def tramp(_user, k, n, done, _rgba):
+            return 1 if (on_pass is not None and on_pass(int(k), int(n), int(done), view)) else 0
+
+        st = Stats()
+        cb = PROGRESS_FN(tramp)              # kept alive for the duration of the call
+        _check(lib().rtiow_render_progressive(self._h, C.byref(cam), C.byref(params), n_passes, cb, None, _p(out), C.byref(st)))
         return out, st.as_dict()
 
     def tile_buffer_bytes(self, params: Params, world: int) -> int:

@@ -363,6 +363,10 @@ template <typename K> static int prep_kernel(K kernel, size_t smem, int threads,
     return RTIOW_OK;
 }
 
+// samples [begin, begin + count) of every pixel: the whole frame is {0, spp}; a progressive pass renders a slice and adds to the
+// accumulators the earlier passes left (rtiow_render_progressive)
+struct SampleRange { uint32_t begin, count; };
+
 // chunks handed out per atomic: up to 256 samples' worth, but small frames get smaller fetches so that every warp of the
 // persistent grid still draws >= 8 of them (a 400x225@10 frame is only ~6 paths per lane: big fetches left warps idle)
 template <typename T> static void size_fetch(RenderArgs<T>& a, int grid, int threads)
@@ -375,21 +379,21 @@ template <typename T> static void size_fetch(RenderArgs<T>& a, int grid, int thr
 
 template <typename T>
 static int launch_render(DeviceState& d, const rtiow_camera* cam, const rtiow_params* p, uint32_t rank, uint32_t world, uint32_t* d_tiles,
-                         cudaStream_t st, uint32_t* launches, uint32_t* peer_frame)
+                         cudaStream_t st, uint32_t* launches, uint32_t* peer_frame, SampleRange sr)
 {
     RenderArgs<T> a;
     a.scene = d.scene; a.cam = to_dev_camera<T>(*cam);
-    a.width = p->width; a.height = p->height; a.spp = p->spp; a.max_depth = p->max_depth; a.t_min = (T)p->t_min; a.key = philox_key(p->seed);
+    a.width = p->width; a.height = p->height; a.spp = sr.count; a.smp_begin = sr.begin; a.max_depth = p->max_depth; a.t_min = (T)p->t_min; a.key = philox_key(p->seed);
     a.inv_wm1 = (T)(1.0 / (double)(p->width - 1)); a.inv_hm1 = (T)(1.0 / (double)(p->height - 1));
     a.rank = rank; a.world = world; a.tile_rows = p->tile_rows; a.local_rows = rows_of_rank(p->height, p->tile_rows, world, rank);
-    a.chunk_samples = std::min<uint32_t>(p->spp, 256u);
-    a.chunks_per_pixel = (p->spp + a.chunk_samples - 1) / a.chunk_samples;
+    a.chunk_samples = std::min<uint32_t>(sr.count, 256u);
+    a.chunks_per_pixel = (sr.count + a.chunk_samples - 1) / a.chunk_samples;
     a.chunks_per_fetch = std::max<uint32_t>(1u, 256u / a.chunk_samples);
     const uint64_t n_lp = (uint64_t)a.local_rows * p->width;
     a.n_chunks = n_lp * a.chunks_per_pixel;
     CU(d.accum.resize(3 * n_lp));
     a.accum = d.accum.p; a.work_counter = d.counters.p; a.ray_counter = d.counters.p + 1; a.np_smem = 1;
-    CU(cudaMemsetAsync(d.accum.p, 0, 3 * n_lp * sizeof(unsigned long long), st));
+    if (sr.begin == 0) CU(cudaMemsetAsync(d.accum.p, 0, 3 * n_lp * sizeof(unsigned long long), st));     // later passes add to the same sums
     CU(cudaMemsetAsync(d.counters.p, 0, 2 * sizeof(unsigned long long), st));
     if (n_lp == 0) return RTIOW_OK;
     int grid = 0;
@@ -431,21 +435,22 @@ static int launch_render(DeviceState& d, const rtiow_camera* cam, const rtiow_pa
     }
     CU(cudaGetLastError());
     if (peer_frame)      // fused quantise + gather: stores go to rank 0's frame through peer memory
-        finalize_to_frame_kernel<<<(unsigned)((n_lp + 255) / 256), 256, 0, st>>>(d.accum.p, (uint32_t)n_lp, p->spp, p->alpha, p->width, p->tile_rows, world, rank, peer_frame);
+        finalize_to_frame_kernel<<<(unsigned)((n_lp + 255) / 256), 256, 0, st>>>(d.accum.p, (uint32_t)n_lp, sr.begin + sr.count, p->alpha, p->width, p->tile_rows, world, rank, peer_frame);
     else
-        finalize_kernel<<<(unsigned)((n_lp + 255) / 256), 256, 0, st>>>(d.accum.p, (uint32_t)n_lp, p->spp, p->alpha, d_tiles);
+        finalize_kernel<<<(unsigned)((n_lp + 255) / 256), 256, 0, st>>>(d.accum.p, (uint32_t)n_lp, sr.begin + sr.count, p->alpha, d_tiles);
     CU(cudaGetLastError());
     *launches += 2;
     return RTIOW_OK;
 }
 
 static int render_tiles(const rtiow_ctx* c, DeviceState& d, const rtiow_camera* cam, const rtiow_params* p, uint32_t rank, uint32_t world, uint32_t* d_tiles,
-                        cudaStream_t st, uint32_t* launches, uint32_t* peer_frame = nullptr)
+                        cudaStream_t st, uint32_t* launches, uint32_t* peer_frame = nullptr, const SampleRange* range = nullptr)
 {
     if (!d.has_scene) return fail(RTIOW_ERR_INVALID_ARG, "no scene uploaded (call rtiow_scene_upload first)");
     CU(cudaSetDevice(d.device));
-    return p->precision == RTIOW_PRECISION_F64 ? launch_render<double>(d, cam, p, rank, world, d_tiles, st, launches, peer_frame)
-                                               : launch_render<float>(d, cam, p, rank, world, d_tiles, st, launches, peer_frame);
+    const SampleRange sr = range ? *range : SampleRange{ 0u, p->spp };
+    return p->precision == RTIOW_PRECISION_F64 ? launch_render<double>(d, cam, p, rank, world, d_tiles, st, launches, peer_frame, sr)
+                                               : launch_render<float>(d, cam, p, rank, world, d_tiles, st, launches, peer_frame, sr);
 }
 
 static double now_ms()
@@ -496,10 +501,10 @@ extern "C" int rtiow_deinterleave_device(rtiow_ctx* c, const void* d_gathered, c
 }
 
 // THE drop-in call (main.rs:122-145)
-extern "C" int rtiow_render(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_params* p, uint8_t* out_rgba, rtiow_stats* stats)
+// One launch per device over the sample range `sr` + the quantise/gather epilogue + the frame to host memory.
+static int render_frame(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_params* p, SampleRange sr, uint8_t* out_rgba, rtiow_stats* stats)
 {
-    if (!c || !cam || !out_rgba) return fail(RTIOW_ERR_INVALID_ARG, "NULL argument");
-    int rc = check_params(p); if (rc) return rc;
+    int rc = RTIOW_OK;
     const double t0 = now_ms();
     const uint32_t world = (uint32_t)c->dev.size();
     const size_t frame_bytes = (size_t)p->width * p->height * 4;
@@ -516,7 +521,7 @@ extern "C" int rtiow_render(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_p
     if (world == 1) {
         CU(d0.tiles.resize(tile_px));
         CU(cudaEventRecord(d0.ev0, d0.stream));
-        rc = render_tiles(c, d0, cam, p, 0, 1, d0.tiles.p, d0.stream, &launches); if (rc) return rc;
+        rc = render_tiles(c, d0, cam, p, 0, 1, d0.tiles.p, d0.stream, &launches, nullptr, &sr); if (rc) return rc;
         CU(cudaEventRecord(d0.ev1, d0.stream));
         d_final = d0.tiles.p;                                  // world == 1: rank-local order IS top-down
     } else {
@@ -531,7 +536,7 @@ extern "C" int rtiow_render(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_p
             uint32_t* dst = nullptr;
             if (!c->peer_ok) { if (r == 0) dst = d0.gathered.p; else { CU(d.tiles.resize(tile_px)); dst = d.tiles.p; } }
             if (r == 0) CU(cudaEventRecord(d.ev0, d.stream));
-            rc = render_tiles(c, d, cam, p, r, world, dst, d.stream, &launches, c->peer_ok ? d0.frame.p : nullptr); if (rc) return rc;
+            rc = render_tiles(c, d, cam, p, r, world, dst, d.stream, &launches, c->peer_ok ? d0.frame.p : nullptr, &sr); if (rc) return rc;
             if (r == 0) CU(cudaEventRecord(d.ev1, d.stream));
             if (r != 0) {
                 if (!c->peer_ok) {
@@ -567,11 +572,50 @@ extern "C" int rtiow_render(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_p
             rays += d.pinned_cnt[1];
         }
         stats->kernel_ms = ms; stats->total_ms = now_ms() - t0;
-        stats->paths = (uint64_t)p->width * p->height * p->spp;
+        stats->paths = (uint64_t)p->width * p->height * sr.count;
         stats->rays_traced = rays; stats->sphere_tests = rays * (uint64_t)d0.scene.n;
         stats->h2d_bytes = sizeof(rtiow_camera) + sizeof(rtiow_params); stats->d2h_bytes = frame_bytes + 16;
         stats->kernel_launches = launches; stats->n_gpus = world;
     }
+    return RTIOW_OK;
+}
+
+extern "C" int rtiow_render(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_params* p, uint8_t* out_rgba, rtiow_stats* stats)
+{
+    if (!c || !cam || !out_rgba) return fail(RTIOW_ERR_INVALID_ARG, "NULL argument");
+    int rc = check_params(p); if (rc) return rc;
+    return render_frame(c, cam, p, SampleRange{ 0u, p->spp }, out_rgba, stats);
+}
+
+// The per-pass preview the reference gets from its progress bar and piston window (main.rs:120-124,151-171): the spp samples
+// are rendered in n_passes slices; after each, the frame so far (quantised with the samples done so far, vec3.rs:404-420)
+// is handed to the callback.  The accumulators are integer sums over the same (pixel, sample) keys, so the last frame is
+// bit-identical to rtiow_render's, and the frame after k passes to rtiow_render with spp = samples done.
+extern "C" int rtiow_render_progressive(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_params* p, uint32_t n_passes, rtiow_progress_fn on_pass,
+                                        void* user, uint8_t* out_rgba, rtiow_stats* stats)
+{
+    if (!c || !cam || !out_rgba) return fail(RTIOW_ERR_INVALID_ARG, "NULL argument");
+    int rc = check_params(p); if (rc) return rc;
+    if (n_passes == 0) return fail(RTIOW_ERR_INVALID_ARG, "n_passes must be >= 1");
+    n_passes = std::min<uint32_t>(n_passes, p->spp);
+    rtiow_stats total; memset(&total, 0, sizeof total);
+    const double t0 = now_ms();
+    uint32_t done = 0;
+    for (uint32_t k = 0; k < n_passes; ++k) {
+        const uint32_t upto = (uint32_t)(((uint64_t)p->spp * (k + 1)) / n_passes);      // passes differ by at most one sample
+        rtiow_stats st;
+        rc = render_frame(c, cam, p, SampleRange{ done, upto - done }, out_rgba, &st); if (rc) return rc;
+        done = upto;
+        total.kernel_ms += st.kernel_ms; total.paths += st.paths; total.rays_traced += st.rays_traced; total.sphere_tests += st.sphere_tests;
+        total.h2d_bytes += st.h2d_bytes; total.d2h_bytes += st.d2h_bytes; total.kernel_launches += st.kernel_launches; total.n_gpus = st.n_gpus;
+        if (on_pass && on_pass(user, k + 1, n_passes, done, out_rgba) != 0 && k + 1 < n_passes) {
+            total.total_ms = now_ms() - t0;
+            if (stats) *stats = total;
+            return fail(RTIOW_ERR_CANCELLED, "cancelled by the progress callback after pass %u of %u (%u of %u spp)", k + 1, n_passes, done, p->spp);
+        }
+    }
+    total.total_ms = now_ms() - t0;
+    if (stats) *stats = total;
     return RTIOW_OK;
 }
 

@@ -15,7 +15,8 @@ namespace rt {
 template <typename T> struct RenderArgs {
     SceneDev scene;
     CameraT<T> cam;
-    uint32_t width, height, spp;
+    uint32_t width, height, spp;   // spp: samples per pixel rendered by THIS launch (a progressive pass renders a slice)
+    uint32_t smp_begin;            // index of the launch's first sample: the Philox key uses smp_begin + local index
     int32_t max_depth;
     T t_min;
     T inv_wm1, inv_hm1;            // 1/(width-1), 1/(height-1): the jitter denominators of main.rs:131-132
@@ -205,7 +206,7 @@ __device__ __forceinline__ bool assign_work(const RenderArgs<T>& a, WorkCursor& 
         if (!busy && !fresh && r < avail) {
             fresh = true;
             acc_lp = wc.c_lp;
-            ps.smp = wc.cs + r;
+            ps.smp = a.smp_begin + wc.cs + r;
             *px = wc.c_x;
             *pj = a.height - 1u - wc.c_y;                            // j = 0 is the bottom row (main.rs:132,141-145)
             ps.pix_key = *pj * a.width + wc.c_x;

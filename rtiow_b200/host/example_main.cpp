@@ -3,7 +3,7 @@
 // into flags.  No preview window (main.rs:151-171 cannot run headless).
 //
 //   rtiow_host_example [--width W] [--height H] [--spp N] [--depth D] [--seed S] [--scene-seed S] [--gpus G]
-//                      [--grid HALF_EXTENT] [--materials 0..3] [--f64] [--out image.png|image.ppm] [--selftest]
+//                      [--grid HALF_EXTENT] [--materials 0..3] [--f64] [--passes N] [--out image.png|image.ppm] [--selftest]
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
@@ -58,6 +58,14 @@ static int selftest()
     catch (const RenderError& e) { expect(e.kind == RenderError::Unsupported, "unknown shape -> RenderError::Unsupported"); }
     try { RenderParams q = p; q.width = 1; render(cam, random_scene(1), q); expect(false, "width 1 must be InvalidArg"); }
     catch (const RenderError& e) { expect(e.kind == RenderError::InvalidArg, "width 1 -> RenderError::InvalidArg"); }
+    // progressive preview: 4 passes of 2 spp; the last frame equals render()'s, the first equals render() at 2 spp
+    { std::vector<uint32_t> seen; std::vector<uint8_t> first;
+      std::vector<uint8_t> c = render_progressive(cam, random_scene(1), p, 4, [&](uint32_t k, uint32_t n, uint32_t done, const std::vector<uint8_t>& f) {
+          seen.push_back(done); if (k == 1) first = f; return n != 4; });
+      RenderParams q = p; q.spp = 2;
+      expect(c == a && seen == std::vector<uint32_t>({ 2, 4, 6, 8 }) && first == render(cam, random_scene(1), q), "render_progressive: passes, preview and final frame");
+      try { render_progressive(cam, random_scene(1), p, 4, [](uint32_t, uint32_t, uint32_t, const std::vector<uint8_t>&) { return true; }); expect(false, "cancel must throw"); }
+      catch (const RenderError& e) { expect(e.kind == RenderError::Cancelled, "callback returning true -> RenderError::Cancelled"); } }
     expect(write_png("/tmp/rtiow_selftest.png", 160, 90, a) && write_ppm("/tmp/rtiow_selftest.ppm", 160, 90, a), "PNG/PPM written");
     std::cout << (bad ? "selftest FAILED\n" : "selftest ok\n");
     return bad ? 1 : 0;
@@ -67,7 +75,7 @@ int main(int argc, char** argv)
 {
     RenderParams p; p.width = 200; p.height = 133;                       // main.rs:24-28
     uint64_t scene_seed = 1; int grid = 11, materials = 0; std::string out = "image.png";     // main.rs:177
-    bool explicit_h = false;
+    bool explicit_h = false; uint32_t passes = 0;
     for (int i = 1; i < argc; ++i) {
         auto next = [&]() -> const char* { if (i + 1 >= argc) { std::cerr << "missing value for " << argv[i] << "\n"; std::exit(2); } return argv[++i]; };
         if (!std::strcmp(argv[i], "--width")) p.width = std::atoi(next());
@@ -80,6 +88,7 @@ int main(int argc, char** argv)
         else if (!std::strcmp(argv[i], "--grid")) grid = std::atoi(next());
         else if (!std::strcmp(argv[i], "--materials")) materials = std::atoi(next());
         else if (!std::strcmp(argv[i], "--f64")) p.f64 = true;
+        else if (!std::strcmp(argv[i], "--passes")) passes = uint32_t(std::atoi(next()));
         else if (!std::strcmp(argv[i], "--out")) out = next();
         else if (!std::strcmp(argv[i], "--selftest")) return selftest();
         else { std::cerr << "unknown flag " << argv[i] << "\n"; return 2; }
@@ -90,7 +99,10 @@ int main(int argc, char** argv)
         Camera cam(Point3(13, 2, 3), Point3(0, 0, 0), Vec3(0, 1, 0), 20.0, double(p.width) / double(p.height), 0.1, 10.0);   // main.rs:108-118
         rtiow_stats st{};
         auto t0 = std::chrono::steady_clock::now();
-        std::vector<uint8_t> pixels = render(cam, world, p, &st);        // main.rs:122-145
+        // main.rs:122-145; with --passes N the progress the reference shows as a bar (main.rs:120,124) is printed per pass
+        std::vector<uint8_t> pixels = passes == 0 ? render(cam, world, p, &st)
+            : render_progressive(cam, world, p, passes, [](uint32_t k, uint32_t n, uint32_t done, const std::vector<uint8_t>&) {
+                  std::cout << "pass " << k << "/" << n << ": " << done << " spp\n"; return false; }, &st);
         double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         std::cout << "\nDone.\n";                                        // main.rs:149
         std::cout << p.width << "x" << p.height << " @ " << p.spp << " spp on " << st.n_gpus << " GPU(s): kernel " << st.kernel_ms << " ms, call " << ms

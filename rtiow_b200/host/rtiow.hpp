@@ -16,6 +16,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <limits>
+#include <functional>
 #include <memory>
 #include <optional>
 #include <ostream>
@@ -267,14 +268,26 @@ struct RenderParams {                                     // runtime form of the
 class RenderError : public std::runtime_error {
 public:
     enum Kind { InvalidArg = RTIOW_ERR_INVALID_ARG, Unsupported = RTIOW_ERR_UNSUPPORTED, Cuda = RTIOW_ERR_CUDA, Nccl = RTIOW_ERR_NCCL,
-                NoDevice = RTIOW_ERR_NO_DEVICE, NoMem = RTIOW_ERR_NOMEM };
+                NoDevice = RTIOW_ERR_NO_DEVICE, NoMem = RTIOW_ERR_NOMEM, Cancelled = RTIOW_ERR_CANCELLED };
     Kind kind;
     RenderError(int code, const std::string& msg) : std::runtime_error(msg), kind(Kind(code)) {}
 };
 
-// render(): replaces main.rs:122-145.  Returns top-down RGBA8, 4*W*H bytes — the Vec<u8> handed to
-// ImageBuffer::from_vec at main.rs:147.  Throws RenderError (Rust: Err(RenderError)); never aborts.
-inline std::vector<uint8_t> render(const Camera& cam, const HittableList& world, const RenderParams& p, rtiow_stats* stats = nullptr)
+// per-pass preview: called with (pass [1-based], n_passes, spp done so far, the frame so far); return true to stop the render
+using ProgressFn = std::function<bool(uint32_t, uint32_t, uint32_t, const std::vector<uint8_t>&)>;
+
+namespace detail {
+struct ProgressCtx { const ProgressFn* fn; const std::vector<uint8_t>* frame; };
+inline int progress_trampoline(void* user, uint32_t pass, uint32_t n_passes, uint32_t spp_done, const uint8_t*)
+{
+    auto* pc = static_cast<ProgressCtx*>(user);
+    return (*pc->fn)(pass, n_passes, spp_done, *pc->frame) ? 1 : 0;
+}
+}  // namespace detail
+
+// The world as the GPU sees it + one render call; n_passes == 0: rtiow_render, else rtiow_render_progressive.
+inline std::vector<uint8_t> render_impl(const Camera& cam, const HittableList& world, const RenderParams& p, rtiow_stats* stats, uint32_t n_passes,
+                                        const ProgressFn* on_pass)
 {
     std::vector<double> cx, cy, cz, rad, ar, ag, ab, prm; std::vector<uint32_t> mi, kind;
     std::vector<const Scatter*> seen;
@@ -301,9 +314,29 @@ inline std::vector<uint8_t> render(const Camera& cam, const HittableList& world,
     rp.width = p.width; rp.height = p.height; rp.spp = p.spp; rp.max_depth = p.max_depth; rp.t_min = p.t_min; rp.seed = p.seed; rp.alpha = p.alpha;
     rp.precision = p.f64 ? RTIOW_PRECISION_F64 : RTIOW_PRECISION_F32; rp.tile_rows = p.tile_rows;
     std::vector<uint8_t> out(size_t(4) * p.width * p.height);
-    check(rtiow_render(ctx, &cam.raw(), &rp, out.data(), stats));
+    if (n_passes == 0) check(rtiow_render(ctx, &cam.raw(), &rp, out.data(), stats));
+    else {
+        detail::ProgressCtx pc{ on_pass, &out };
+        check(rtiow_render_progressive(ctx, &cam.raw(), &rp, n_passes, on_pass && *on_pass ? detail::progress_trampoline : nullptr, &pc, out.data(), stats));
+    }
     rtiow_ctx_destroy(ctx);
     return out;
+}
+
+// render(): replaces main.rs:122-145.  Returns top-down RGBA8, 4*W*H bytes — the Vec<u8> handed to
+// ImageBuffer::from_vec at main.rs:147.  Throws RenderError (Rust: Err(RenderError)); never aborts.
+inline std::vector<uint8_t> render(const Camera& cam, const HittableList& world, const RenderParams& p, rtiow_stats* stats = nullptr)
+{
+    return render_impl(cam, world, p, stats, 0, nullptr);
+}
+
+// render_progressive(): the same frame in n_passes slices of the samples, with a preview after each — what the reference's
+// progress bar (main.rs:120,124) and preview window (main.rs:151-171) are for.  The returned frame is bit-identical to
+// render()'s.  A callback that returns true stops the render: RenderError::Cancelled.
+inline std::vector<uint8_t> render_progressive(const Camera& cam, const HittableList& world, const RenderParams& p, uint32_t n_passes,
+                                               const ProgressFn& on_pass, rtiow_stats* stats = nullptr)
+{
+    return render_impl(cam, world, p, stats, n_passes ? n_passes : 1, &on_pass);
 }
 
 // random_scene (main.rs:59-102) with an explicit seed

@@ -6,7 +6,7 @@
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_int, c_void};
 
-pub const RTIOW_ABI_VERSION: c_int = 1;
+pub const RTIOW_ABI_VERSION: c_int = 2;
 
 pub const RTIOW_OK: c_int = 0;
 pub const RTIOW_ERR_INVALID_ARG: c_int = -1;
@@ -15,6 +15,7 @@ pub const RTIOW_ERR_CUDA: c_int = -3;
 pub const RTIOW_ERR_NCCL: c_int = -4;
 pub const RTIOW_ERR_NO_DEVICE: c_int = -5;
 pub const RTIOW_ERR_NOMEM: c_int = -6;
+pub const RTIOW_ERR_CANCELLED: c_int = -7;
 
 pub const RTIOW_MAT_LAMBERTIAN: u32 = 0;
 pub const RTIOW_MAT_METAL: u32 = 1;
@@ -72,6 +73,9 @@ pub struct rtiow_stats {
     pub kernel_launches: u32, pub n_gpus: u32,
 }
 
+/// int (*)(void* user, uint32_t pass, uint32_t n_passes, uint32_t spp_done, const uint8_t* rgba); non-zero return cancels
+pub type rtiow_progress_fn = unsafe extern "C" fn(user: *mut c_void, pass: u32, n_passes: u32, spp_done: u32, rgba: *const u8) -> c_int;
+
 extern "C" {
     pub fn rtiow_abi_version() -> c_int;
     pub fn rtiow_last_error() -> *const c_char;
@@ -85,6 +89,8 @@ extern "C" {
     pub fn rtiow_params_default(p: *mut rtiow_params);
     pub fn rtiow_render(ctx: *mut rtiow_ctx, cam: *const rtiow_camera, p: *const rtiow_params, out_rgba: *mut u8,
                         stats: *mut rtiow_stats) -> c_int;
+    pub fn rtiow_render_progressive(ctx: *mut rtiow_ctx, cam: *const rtiow_camera, p: *const rtiow_params, n_passes: u32,
+                                    on_pass: Option<rtiow_progress_fn>, user: *mut c_void, out_rgba: *mut u8, stats: *mut rtiow_stats) -> c_int;
     pub fn rtiow_tile_buffer_bytes(p: *const rtiow_params, world: c_int, out_bytes: *mut usize) -> c_int;
     pub fn rtiow_render_tiles_device(ctx: *mut rtiow_ctx, cam: *const rtiow_camera, p: *const rtiow_params, rank: c_int, world: c_int,
                                      d_tiles: *mut c_void, stream: *mut c_void, stats: *mut rtiow_stats) -> c_int;

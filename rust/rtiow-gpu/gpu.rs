@@ -34,7 +34,7 @@ impl Default for RenderParams {
 }
 
 #[derive(Debug)]
-pub enum RenderError { InvalidArg(String), Unsupported(String), Cuda(String), Nccl(String), NoDevice(String), NoMem(String) }
+pub enum RenderError { InvalidArg(String), Unsupported(String), Cuda(String), Nccl(String), NoDevice(String), NoMem(String), Cancelled(String) }
 
 fn err(code: i32) -> RenderError {
     let msg = unsafe { CStr::from_ptr(sys::rtiow_last_error()) }.to_string_lossy().into_owned();
@@ -44,6 +44,7 @@ fn err(code: i32) -> RenderError {
         sys::RTIOW_ERR_NCCL => RenderError::Nccl(msg),
         sys::RTIOW_ERR_NO_DEVICE => RenderError::NoDevice(msg),
         sys::RTIOW_ERR_NOMEM => RenderError::NoMem(msg),
+        sys::RTIOW_ERR_CANCELLED => RenderError::Cancelled(msg),
         _ => RenderError::InvalidArg(msg),
     }
 }
@@ -54,6 +55,25 @@ impl Drop for Ctx { fn drop(&mut self) { unsafe { sys::rtiow_ctx_destroy(self.0)
 /// Replaces main.rs:122-145.  Returns top-down RGBA8, `4*width*height` bytes: exactly the `Vec<u8>` handed to
 /// `ImageBuffer::from_vec(IMAGE_WIDTH, IMAGE_HEIGHT, pixels)` at main.rs:147.
 pub fn render(cam: &Camera, world: &HittableList, p: &RenderParams) -> Result<Vec<u8>, RenderError> {
+    render_impl(cam, world, p, 0, None)
+}
+
+/// The same frame in `n_passes` slices of the samples, with the frame so far handed to `on_pass(pass, n_passes, spp_done, rgba)`
+/// after each — the role of the indicatif bar (main.rs:120,124) and the piston preview window (main.rs:151-171).  The returned
+/// frame is bit-identical to `render`'s.  `on_pass` returning `true` stops the render: `Err(RenderError::Cancelled)`.
+pub fn render_progressive(cam: &Camera, world: &HittableList, p: &RenderParams, n_passes: u32,
+                          on_pass: &mut dyn FnMut(u32, u32, u32, &[u8]) -> bool) -> Result<Vec<u8>, RenderError> {
+    render_impl(cam, world, p, n_passes.max(1), Some(on_pass))
+}
+
+struct Progress<'a> { f: &'a mut dyn FnMut(u32, u32, u32, &[u8]) -> bool, len: usize }
+unsafe extern "C" fn progress_trampoline(user: *mut std::os::raw::c_void, pass: u32, n_passes: u32, spp_done: u32, rgba: *const u8) -> std::os::raw::c_int {
+    let p = &mut *(user as *mut Progress);
+    (p.f)(pass, n_passes, spp_done, std::slice::from_raw_parts(rgba, p.len)) as std::os::raw::c_int
+}
+
+fn render_impl(cam: &Camera, world: &HittableList, p: &RenderParams, n_passes: u32,
+               on_pass: Option<&mut dyn FnMut(u32, u32, u32, &[u8]) -> bool>) -> Result<Vec<u8>, RenderError> {
     // flatten the trait objects through the provided describe() methods; unknown ones are an error, not a CPU fallback
     let (mut cx, mut cy, mut cz, mut radius, mut mat_index) = (vec![], vec![], vec![], vec![], vec![]);
     let (mut kind, mut ar, mut ag, mut ab, mut param) = (vec![], vec![], vec![], vec![], vec![]);
@@ -82,7 +102,15 @@ pub fn render(cam: &Camera, world: &HittableList, p: &RenderParams) -> Result<Ve
         prm.width = p.width; prm.height = p.height; prm.spp = p.spp; prm.max_depth = p.max_depth; prm.t_min = p.t_min;
         prm.seed = p.seed; prm.alpha = p.alpha;
         let mut pixels = vec![0u8; 4 * p.width as usize * p.height as usize];
-        let rc = sys::rtiow_render(ctx.0, &cam.raw(), &prm, pixels.as_mut_ptr(), ptr::null_mut());
+        let rc = match on_pass {
+            None if n_passes == 0 => sys::rtiow_render(ctx.0, &cam.raw(), &prm, pixels.as_mut_ptr(), ptr::null_mut()),
+            None => sys::rtiow_render_progressive(ctx.0, &cam.raw(), &prm, n_passes, None, ptr::null_mut(), pixels.as_mut_ptr(), ptr::null_mut()),
+            Some(f) => {
+                let mut pr = Progress { f, len: pixels.len() };
+                sys::rtiow_render_progressive(ctx.0, &cam.raw(), &prm, n_passes, Some(progress_trampoline),
+                                              &mut pr as *mut Progress as *mut std::os::raw::c_void, pixels.as_mut_ptr(), ptr::null_mut())
+            }
+        };
         if rc != sys::RTIOW_OK { return Err(err(rc)); }
         Ok(pixels)
     }

@@ -132,6 +132,7 @@ def test_invalid_arguments_do_not_crash(capi):
     assert L.rtiow_ctx_create(0, C.byref(h)) == capi.ERR_INVALID_ARG and b"n_gpus" in L.rtiow_last_error()
     assert L.rtiow_scene_upload(None, None, None) == capi.ERR_INVALID_ARG
     assert L.rtiow_render(None, None, None, None, None) == capi.ERR_INVALID_ARG
+    assert L.rtiow_render_progressive(None, None, None, 4, capi.PROGRESS_FN(0), None, None, None) == capi.ERR_INVALID_ARG
     assert L.rtiow_camera_new(None, None, None, 1.0, 1.0, 1.0, 1.0, None) == capi.ERR_INVALID_ARG
     assert L.rtiow_tile_buffer_bytes(None, 1, None) == capi.ERR_INVALID_ARG
     n = C.c_size_t(0)

@@ -107,6 +107,36 @@ def test_determinism_and_seed(ctx_final, capi):
     assert not np.array_equal(a, c) and rmse(a, c) < 15
 
 
+@pytest.mark.parametrize("prec", [0, 1])
+def test_progressive_passes_are_prefixes_of_the_frame(ctx_final, capi, prec):
+    """rtiow_render_progressive (the per-pass preview that stands in for main.rs:120-124,151-171): the
+    accumulators are integer sums over (pixel, sample) keys, so the frame after k passes is BIT-IDENTICAL to rtiow_render with
+    spp = samples done, the last one to the full render; stats add up; a callback returning true cancels."""
+    cam = final_camera(capi, 16 / 9)
+    kw = dict(width=320, height=180, seed=3, precision=prec)
+    spp, passes = 13, 4                                                   # uneven slices: 3, 3, 3, 4
+    full, st_full = ctx_final.render(cam, capi.default_params(spp=spp, **kw))
+    seen = []
+    def on_pass(k, n, done, frame):
+        seen.append((k, n, done, frame.copy()))
+        return False
+    img, st = ctx_final.render_progressive(cam, capi.default_params(spp=spp, **kw), passes, on_pass)
+    assert [(k, n, d) for k, n, d, _ in seen] == [(1, 4, 3), (2, 4, 6), (3, 4, 9), (4, 4, 13)]
+    assert np.array_equal(img, full) and np.array_equal(seen[-1][3], full)
+    assert st["rays_traced"] == st_full["rays_traced"] and st["paths"] == st_full["paths"] and st["kernel_launches"] == 2 * passes
+    for k, n, done, frame in seen[:-1]:
+        part, _ = ctx_final.render(cam, capi.default_params(spp=done, **kw))
+        assert np.array_equal(frame, part), f"preview after pass {k} differs from a {done}-spp render"
+    # more passes than samples: clamped to one sample per pass; no callback at all is allowed
+    img2, st2 = ctx_final.render_progressive(cam, capi.default_params(spp=2, **kw), 50)
+    assert st2["kernel_launches"] == 4 and np.array_equal(img2, ctx_final.render(cam, capi.default_params(spp=2, **kw))[0])
+    # cancel after the second pass: the error is reported, the buffer keeps the frame so far
+    out = np.zeros((180, 320, 4), np.uint8)
+    with pytest.raises(capi.RtiowError) as e:
+        ctx_final.render_progressive(cam, capi.default_params(spp=spp, **kw), passes, lambda k, n, done, frame: k == 2, out=out)
+    assert e.value.code == capi.ERR_CANCELLED and np.array_equal(out, seen[1][3])
+
+
 @pytest.mark.parametrize("W,H,spp", [(1200, 675, 2), (400, 225, 10), (201, 133, 3)])
 def test_tile_partition_invariance(ctx_final, capi, W, H, spp):
     """N-GPU image == 1-GPU image, bit for bit: ranks are emulated one after another on this GPU through the
