@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — Mpaths/s of the rtiow render hot path on B200 (BASELINE.json metric), one JSON line.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg1|cfg2|cfg3-*|cfg4|cfg5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
            bench.py --gpus N --steps K --warmup W
 
@@ -35,6 +35,17 @@ os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's version ba
 
 WORKLOAD = dict(name="RTIOW Part 1 final scene (seeded random_scene), 1200x675, 500 spp, depth 50", width=1200, height=675, spp=500,
                 max_depth=50, t_min=1e-4, scene_seed=1, sample_seed=1)
+# BASELINE.json configs by name; the default (and the line the driver records) is cfg2 = configs[1].  The others are parity-test
+# cases (tests/test_full_size_gpu.py) that can also be timed: (workload name, width, height, spp, grid half-extent, material mode)
+CONFIGS = {
+    "cfg1": ("RTIOW Part 1 final scene (seeded random_scene), 400x225, 10 spp, depth 50", 400, 225, 10, 11, 0),
+    "cfg2": (WORKLOAD["name"], 1200, 675, 500, 11, 0),
+    "cfg3-lambertian": ("material isolation: all-Lambertian, 800x450, 100 spp, depth 50", 800, 450, 100, 11, 1),
+    "cfg3-metal": ("material isolation: all-Metal (fuzz), 800x450, 100 spp, depth 50", 800, 450, 100, 11, 2),
+    "cfg3-dielectric": ("material isolation: all-Dialectric + hollow glass shell, 800x450, 100 spp, depth 50", 800, 450, 100, 11, 3),
+    "cfg4": ("random-spheres scene scaled to 10k spheres (grid -50..=50), 1920x1080, 256 spp, depth 50", 1920, 1080, 256, 50, 0),
+    "cfg5": ("RTIOW Part 1 final scene (seeded random_scene), 3840x2160, 1024 spp, depth 50", 3840, 2160, 1024, 11, 0),
+}
 FLOP_PER_TEST = 17.0            # sphere.rs:18-25 with a and r^2 hoisted
 FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE render_kernel launch of this workload on one GPU, from the ncu --set full
@@ -49,13 +60,19 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--width", type=int, default=WORKLOAD["width"])
-    ap.add_argument("--height", type=int, default=WORKLOAD["height"])
-    ap.add_argument("--spp", type=int, default=WORKLOAD["spp"])
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS), help="BASELINE.json configuration (default: configs[1], the headline)")
+    ap.add_argument("--width", type=int, default=None)
+    ap.add_argument("--height", type=int, default=None)
+    ap.add_argument("--spp", type=int, default=None)
     ap.add_argument("--tile-rows", type=int, default=1)
     ap.add_argument("--cpu-sample-spp", type=int, default=0, help="spp of the bounded CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    a = ap.parse_args()
+    name, w, h, spp, grid, mode = CONFIGS[a.config]
+    a.workload = name if (a.width, a.height, a.spp) == (None, None, None) else f"{name} [overridden size]"
+    a.width, a.height, a.spp = a.width or w, a.height or h, a.spp or spp
+    a.grid, a.material_mode = grid, mode
+    return a
 
 
 # ----------------------------------------------------------------------------------------------- clocks
@@ -121,8 +138,8 @@ def run_reference(args, rank):
         return
     from rtiow_b200 import capi
     W, H = args.width, args.height
-    o, sc = oracle_world(capi.random_scene(WORKLOAD["scene_seed"]))
-    spp = args.cpu_sample_spp or 4
+    o, sc = oracle_world(capi.random_scene(WORKLOAD["scene_seed"], args.grid, args.material_mode))
+    spp = args.cpu_sample_spp or (4 if sc.n < 2000 else 1)
     cores = o.host_threads()
     for _ in range(args.warmup):
         time_oracle(o, sc, W, H, 1, 1)
@@ -135,7 +152,7 @@ def run_reference(args, rank):
     print(json.dumps({
         "impl": "reference", "metric": "Mpaths/s", "value": v, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": {"workload": WORKLOAD["name"], "width": W, "height": H, "spp": args.spp,
+        "dtype": "f64", "data": "synthetic", "config": {"workload": args.workload, "width": W, "height": H, "spp": args.spp,
                                                           "max_depth": 50, "n_spheres": sc.n, "scene_seed": 1},
         "cpu_baseline": {"value": v, "unit": "Mpaths/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -155,7 +172,7 @@ def run_ours(args, rank, local_rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     W, H, spp = args.width, args.height, args.spp
-    scene = capi.random_scene(WORKLOAD["scene_seed"])
+    scene = capi.random_scene(WORKLOAD["scene_seed"], args.grid, args.material_mode)
     n_spheres = len(scene["radius"])
     ctx = capi.Context(device=local_rank)
     ctx.upload_scene(**scene)
@@ -267,7 +284,7 @@ def run_ours(args, rank, local_rank, world):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         o, sc = oracle_world(scene)
         cores = o.host_threads()
-        s_spp = args.cpu_sample_spp or max(2, min(spp, int(2 * cores)))            # ~10-20 s of CPU work
+        s_spp = args.cpu_sample_spp or max(1, min(spp, int(2 * cores * (1200 * 675) / (W * H) * 530 / n_spheres)))   # ~10-30 s of CPU work
         v, dt, _ = time_oracle(o, sc, W, H, s_spp, 1)
         cpu = {"value": v, "unit": "Mpaths/s", "cores": cores, "kind": "port",
                "sample": f"{W}x{H} @ {s_spp} spp ({W * H * s_spp / 1e6:.1f} M paths, {dt:.1f} s) of the {spp} spp workload; f64 C restatement, OpenMP rows"}
@@ -279,7 +296,7 @@ def run_ours(args, rank, local_rank, world):
         out = {
             "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD["name"], "width": W, "height": H, "spp": spp, "max_depth": WORKLOAD["max_depth"], "n_spheres": n_spheres,
+            "config": {"workload": args.workload, "width": W, "height": H, "spp": spp, "max_depth": WORKLOAD["max_depth"], "n_spheres": n_spheres,
                        "scene_seed": WORKLOAD["scene_seed"], "sample_seed": WORKLOAD["sample_seed"], "tile_rows": args.tile_rows,
                        "parallelism": f"interleaved row tiles x{world}" + (", NCCL all-gather" if world > 1 else ""),
                        "l2": "256 MiB device buffer rewritten between timed steps (inside the timed region, ~0.1 ms)"},
@@ -288,8 +305,8 @@ def run_ours(args, rank, local_rank, world):
                     "h2d_bytes_per_step": scene_bytes + 176 + 48, "d2h_bytes_per_step": W * H * 4 + 16},
             "gpu_launches": n_launch,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
-                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (world == 1 and (W, H, spp) == (1200, 675, 500)) else None, "traffic_unit": "bytes/launch (ncu)",
-                         "kernel": "rt::render_kernel<float,true,256,3>", "kernel_ms": kms, "flop_per_test": FLOP_PER_TEST,
+                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (world == 1 and args.config == "cfg2" and (W, H, spp) == (1200, 675, 500)) else None, "traffic_unit": "bytes/launch (ncu)",
+                         "kernel": "rt::render_kernel<float,true,256,3>" if n_spheres < 2500 else "rt::render_kernel<float,true,512,1>", "kernel_ms": kms, "flop_per_test": FLOP_PER_TEST,
                          "rays_per_path": rays_total / paths, "sphere_tests_per_launch": rays_total * n_spheres / world,
                          "peak_source": "FFMA2 calibration kernel in this run (rtiow_fp32_peak_probe, ~300 ms); MEASURED_PEAKS.json has no FP32 entry",
                          "peak_scalar_ffma": peak_scalar_tflops, "peak_nominal": FP32_NOMINAL_TFLOPS},
