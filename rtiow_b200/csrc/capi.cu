@@ -367,14 +367,17 @@ template <typename K> static int prep_kernel(K kernel, size_t smem, int threads,
 // accumulators the earlier passes left (rtiow_render_progressive)
 struct SampleRange { uint32_t begin, count; };
 
-// chunks handed out per atomic: up to 256 samples' worth, but small frames get smaller fetches so that every warp of the
-// persistent grid still draws >= 8 of them (a 400x225@10 frame is only ~6 paths per lane: big fetches left warps idle)
+// Work is handed out in chunks of <= 64 samples of one pixel (two rounds of a warp's 32 lanes).  A fetch from the global
+// counter takes up to 256 samples' worth of chunks, less on small frames (every warp of the persistent grid should draw
+// >= 8 fetches: a 400x225@10 frame is only ~8 paths per lane) and towards the end of any frame (guided_div, rt_render.cuh).
 template <typename T> static void size_fetch(RenderArgs<T>& a, int grid, int threads)
 {
     const uint64_t n_warps = (uint64_t)grid * threads / 32;
     const uint64_t want = a.n_chunks / std::max<uint64_t>(1, n_warps * 8);
     const uint64_t cap = std::max<uint32_t>(1u, 256u / a.chunk_samples);
     a.chunks_per_fetch = (uint32_t)std::min<uint64_t>(cap, std::max<uint64_t>(1, want));
+    a.guided_div = (uint32_t)std::max<uint64_t>(1, 2 * n_warps);
+    if (const char* t = getenv("RTIOW_TUNE_GUIDED")) a.guided_div = (uint32_t)std::max(1, atoi(t));   // experiment knob (tools/): 1 = off
 }
 
 template <typename T>
@@ -386,7 +389,7 @@ static int launch_render(DeviceState& d, const rtiow_camera* cam, const rtiow_pa
     a.width = p->width; a.height = p->height; a.spp = sr.count; a.smp_begin = sr.begin; a.max_depth = p->max_depth; a.t_min = (T)p->t_min; a.key = philox_key(p->seed);
     a.inv_wm1 = (T)(1.0 / (double)(p->width - 1)); a.inv_hm1 = (T)(1.0 / (double)(p->height - 1));
     a.rank = rank; a.world = world; a.tile_rows = p->tile_rows; a.local_rows = rows_of_rank(p->height, p->tile_rows, world, rank);
-    a.chunk_samples = std::min<uint32_t>(sr.count, 256u);
+    a.chunk_samples = std::min<uint32_t>(sr.count, getenv("RTIOW_TUNE_CHUNK") ? (uint32_t)atoi(getenv("RTIOW_TUNE_CHUNK")) : 64u);
     a.chunks_per_pixel = (sr.count + a.chunk_samples - 1) / a.chunk_samples;
     a.chunks_per_fetch = std::max<uint32_t>(1u, 256u / a.chunk_samples);
     const uint64_t n_lp = (uint64_t)a.local_rows * p->width;

@@ -25,7 +25,8 @@ template <typename T> struct RenderArgs {
     uint32_t rank, world, tile_rows, local_rows;
     uint32_t chunk_samples;        // samples per chunk (<= spp); chunks never straddle pixels
     uint32_t chunks_per_pixel;
-    uint32_t chunks_per_fetch;
+    uint32_t chunks_per_fetch;     // chunks per fetch from the work counter while plenty are left ...
+    uint32_t guided_div;           // ... and (chunks left) / guided_div towards the end (guided_div = 2 x warps of the grid)
     uint64_t n_chunks;
     unsigned long long* accum;     // [3][local_rows*width] 32.32 fixed-point radiance sums
     unsigned long long* work_counter;
@@ -187,10 +188,17 @@ __device__ __forceinline__ bool assign_work(const RenderArgs<T>& a, WorkCursor& 
     while (need && !wc.exhausted) {
         if (wc.cs == wc.ce) {
             if (wc.cc == wc.cce) {
-                unsigned long long base = 0;
-                if (lt_mask == 0u) base = atomicAdd(a.work_counter, (unsigned long long)a.chunks_per_fetch);      // lane 0
+                // guided self-scheduling: a fetch takes chunks_per_fetch chunks while plenty are left and 1/guided_div of the
+                // rest towards the end of the frame, so that the warps of the persistent grid run dry together
+                unsigned long long base = 0, take = a.chunks_per_fetch;
+                if (lt_mask == 0u) {                                                                             // lane 0
+                    const unsigned long long seen = *(volatile unsigned long long*)a.work_counter;
+                    const unsigned long long left = a.n_chunks > seen ? a.n_chunks - seen : 0ull;
+                    take = min(take, max(1ull, left / a.guided_div));
+                    base = atomicAdd(a.work_counter, take);
+                }
                 wc.cc = __shfl_sync(RT_FULL, base, 0);
-                wc.cce = wc.cc + a.chunks_per_fetch; if (wc.cce > a.n_chunks) wc.cce = a.n_chunks;
+                wc.cce = wc.cc + __shfl_sync(RT_FULL, take, 0); if (wc.cce > a.n_chunks) wc.cce = a.n_chunks;
                 if (wc.cc >= a.n_chunks) { wc.exhausted = true; break; }
             }
             const unsigned long long c = wc.cc++;
