@@ -306,7 +306,7 @@ def run_ours(args, rank, local_rank, world):
             "gpu_launches": n_launch,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
                          "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (world == 1 and args.config == "cfg2" and (W, H, spp) == (1200, 675, 500)) else None, "traffic_unit": "bytes/launch (ncu)",
-                         "kernel": "rt::render_kernel<float,true,256,3>" if n_spheres < 2500 else "rt::render_kernel<float,true,512,1>", "kernel_ms": kms, "flop_per_test": FLOP_PER_TEST,
+                         "kernel": "rt::render_kernel<float,true,256,3>" if n_spheres < 2500 else "rt::render_kernel<float,true,768,1>", "kernel_ms": kms, "flop_per_test": FLOP_PER_TEST,
                          "rays_per_path": rays_total / paths, "sphere_tests_per_launch": rays_total * n_spheres / world,
                          "peak_source": "FFMA2 calibration kernel in this run (rtiow_fp32_peak_probe, ~300 ms); MEASURED_PEAKS.json has no FP32 entry",
                          "peak_scalar_ffma": peak_scalar_tflops, "peak_nominal": FP32_NOMINAL_TFLOPS},

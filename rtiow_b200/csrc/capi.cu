@@ -424,6 +424,12 @@ static int launch_render(DeviceState& d, const rtiow_camera* cam, const rtiow_pa
             int rc = prep_kernel(k, cfg.smem, 256, d.sms, &grid); if (rc) return rc;
             size_fetch(a, grid, 256);
             k<<<grid, 256, cfg.smem, st>>>(a);
+        } else if (cfg.variant == 1 && cfg.smem - cand_bytes(512) + cand_bytes(768) <= 227 * 1024) {
+            auto k = render_kernel<T, true, 768, 1>;              // one CTA per SM, 24 warps at 80 registers (+2.5 % over 512 threads at 104)
+            const size_t sm = cfg.smem - cand_bytes(512) + cand_bytes(768);
+            int rc = prep_kernel(k, sm, 768, d.sms, &grid); if (rc) return rc;
+            size_fetch(a, grid, 768);
+            k<<<grid, 768, sm, st>>>(a);
         } else if (cfg.variant == 1) {
             auto k = render_kernel<T, true, 512, 1>;
             int rc = prep_kernel(k, cfg.smem, 512, d.sms, &grid); if (rc) return rc;
