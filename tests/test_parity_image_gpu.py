@@ -107,6 +107,30 @@ def test_determinism_and_seed(ctx_final, capi):
     assert not np.array_equal(a, c) and rmse(a, c) < 15
 
 
+def test_scene_too_large_for_shared_memory(ctx, capi, oracle, scene_factory):
+    """16 k spheres (grid -63..=63): the filter table (257 KB) fits no CTA's shared memory, the scan streams it from global
+    memory (L1/L2) — same code, third launch configuration.  Closest hits and a tiny frame against the oracle."""
+    arrays, sc = scene_factory(seed=5, half_extent=63)
+    assert sc.n > 15_000
+    ctx.upload_scene(**arrays)
+    rng = np.random.default_rng(2)
+    n = 4000
+    k = rng.integers(1, sc.n, n)
+    u = rng.normal(size=(n, 3)); u[:, 1] = np.abs(u[:, 1]) + 0.05; u /= np.linalg.norm(u, axis=1, keepdims=True)
+    o = np.asarray(arrays["center"])[k] + u * rng.uniform(1, 60, (n, 1)); d = -u + rng.normal(size=(n, 3)) * 0.02
+    o32, d32 = o.astype(np.float32).astype(np.float64), d.astype(np.float32).astype(np.float64)
+    ref = oracle.world_hit_batch(sc, o32, d32)
+    got = ctx.hitlist_batch(o32, d32, 1e-4)
+    want = np.where(ref["hit"] == 1, ref["index"], -1)
+    assert (got["index"] == want).mean() > 0.995 and (want > 0).mean() > 0.25
+    W, H, spp = 96, 54, 2
+    ref_img, _, cnt = oracle.render(sc, final_camera(oracle, W / H), W, H, spp, seed=8, sampler=oracle.SAMPLER_DIRECT)
+    img, st = render_gpu(ctx, capi, final_camera(capi, W / H), width=W, height=H, spp=spp, seed=8)
+    diff = np.abs(img[..., :3].astype(int) - ref_img[..., :3].astype(int)).max(axis=2)
+    assert (diff <= 1).mean() > 0.99
+    assert abs(st["rays_traced"] / cnt["rays"] - 1) < 1e-2
+
+
 @pytest.mark.parametrize("prec", [0, 1])
 def test_progressive_passes_are_prefixes_of_the_frame(ctx_final, capi, prec):
     """rtiow_render_progressive (the per-pass preview that stands in for main.rs:120-124,151-171): the
