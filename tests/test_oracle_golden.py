@@ -40,6 +40,26 @@ def test_png_sky_rows(oracle, final_scene, sampler):
     assert img[rows[0], 0, 0] <= img[rows[-1], 0, 0]
 
 
+@pytest.mark.parametrize("sampler", ["direct", "rejection"])
+def test_png_big_spheres(oracle, sampler):
+    """The non-random part of random_scene (ground + glass / Lambertian / Metal unit spheres, main.rs:62-64,93-99) as the
+    reference itself rendered it: the oracle reproduces the metal sphere's sky-mirroring cap to a quarter of an LSB (391 block
+    means: get_ray, Sphere::hit, Metal::scatter, the recursion, sky, to_rgba), the sky seen THROUGH the glass sphere
+    (Dialectric::scatter: two refractions + Schlick) and the top of the diffuse sphere (Lambertian::scatter) within the few LSB by
+    which the reference's random small spheres shade them (tests/golden/make_png_big_spheres_fixture.py)."""
+    g = json.load(open(GOLDEN / "png_big_spheres.json"))
+    s = g["scene"]
+    sc = oracle.Scene(s["center"], s["radius"], [0, 1, 2, 3], s["mat_kind"], s["mat_albedo"], s["mat_param"])
+    cam = oracle.camera_new(**{k: v for k, v in g["camera"].items() if k != "cite"})
+    ys = [b[1] for r in g["regions"].values() for b in r["blocks_x_y_r_g_b"]]
+    img, _, _ = oracle.render(sc, cam, g["width"], g["height"], spp=96, seed=7, rows=(min(ys) - 4, max(ys) + 5),
+                              sampler=oracle.SAMPLER_DIRECT if sampler == "direct" else oracle.SAMPLER_REJECTION)
+    for name, r in g["regions"].items():
+        lo, hi = r["tolerance_lsb_lo_hi"]
+        d = np.array([img[y - 4:y + 5, x - 4:x + 5, :3].reshape(-1, 3).astype(float).mean(0) - np.array(c) for x, y, *c in r["blocks_x_y_r_g_b"]])
+        assert len(d) >= 30 and lo <= d.min() and d.max() <= hi, f"{name}: block means differ from the reference PNG by {d.min():.2f} .. {d.max():.2f} LSB"
+
+
 def test_png_corner_pixels_exact(oracle):
     """(0,0),(600,0),(1199,0) -> [220,235,255]; (0,39) -> [221,235,255]."""
     cam = final_camera(oracle, 1.5)

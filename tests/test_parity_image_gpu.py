@@ -107,6 +107,24 @@ def test_determinism_and_seed(ctx_final, capi):
     assert not np.array_equal(a, c) and rmse(a, c) < 15
 
 
+@pytest.mark.parametrize("prec", [0, 1])
+def test_png_big_spheres_gpu(ctx, capi, prec):
+    """the GPU render against the reference's OWN render (rtiow_part1_final.png), on the part of random_scene that is not
+    random: metal cap to a quarter of an LSB, refracted sky and diffuse top within the shading of the reference's random
+    neighbourhood — same fixture and bounds as the oracle's test (tests/test_oracle_golden.py::test_png_big_spheres)"""
+    import json
+    from conftest import ROOT
+    g = json.load(open(ROOT / "tests" / "golden" / "png_big_spheres.json"))
+    s = g["scene"]
+    ctx.upload_scene(s["center"], s["radius"], [0, 1, 2, 3], s["mat_kind"], s["mat_albedo"], s["mat_param"])
+    cam = capi.camera_new(**{k: v for k, v in g["camera"].items() if k != "cite"})
+    img, _ = render_gpu(ctx, capi, cam, width=g["width"], height=g["height"], spp=128, seed=7, precision=prec)
+    for name, r in g["regions"].items():
+        lo, hi = r["tolerance_lsb_lo_hi"]
+        d = np.array([img[y - 4:y + 5, x - 4:x + 5, :3].reshape(-1, 3).astype(float).mean(0) - np.array(c) for x, y, *c in r["blocks_x_y_r_g_b"]])
+        assert lo <= d.min() and d.max() <= hi, f"{name}: block means differ from the reference PNG by {d.min():.2f} .. {d.max():.2f} LSB"
+
+
 def test_scene_too_large_for_shared_memory(ctx, capi, oracle, scene_factory):
     """16 k spheres (grid -63..=63): the filter table (257 KB) fits no CTA's shared memory, the scan streams it from global
     memory (L1/L2) — same code, third launch configuration.  Closest hits and a tiny frame against the oracle."""
