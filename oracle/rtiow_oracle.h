@@ -18,7 +18,9 @@
  *   - the sky seen through the fixed glass sphere (main.rs:93-94): Dialectric::scatter (refract, Schlick) —
  *     49 block means within -1.0 .. +2.5 LSB; and the top of the fixed Lambertian sphere (main.rs:95-96):
  *     Lambertian::scatter — 35 block means within -0.5 .. +4.5 LSB (the reference's random neighbourhood
- *     shades both slightly; tests/golden/png_big_spheres.json, generator committed).
+ *     shades both slightly; tests/golden/png_big_spheres.json, generator committed);
+ *   - the defocused horizon band beside the sphere field: the f64 ground sphere at grazing incidence, the thin
+ *     lens and the Lambertian ground under open sky — 132 block means within 2.5 LSB, unbiased (|mean| <= 0.4).
  * What stays **parity unpinned** by the reference: Metal fuzz > 0 (the fixed sphere has fuzz 0), total
  * internal reflection and the exact rejection-sampler streams (thread_rng is unseedable), and `t` /
  * front_face as separate outputs; those are checked against analytic known answers and an independently

@@ -13,6 +13,10 @@ is the camera (main.rs:108-118).  Three regions of the reference's render theref
          a few per cent of its light are reflections of the random neighbourhood
   brown  the sky-facing top of the diffuse sphere: Lambertian::scatter + albedo; the random neighbourhood only darkens it slightly
 
+  horizon  the defocused transition from sky to the far ground, left and right of the sphere field: the f64 ground sphere
+         (main.rs:62-64) hit at grazing incidence, the thin lens (camera.rs:47-54: the horizon is far out of focus) and the Lambertian
+         ground under the open sky; columns are kept where the PNG shows the bare far-ground colour below the band
+
 We keep 9x9-pixel block means (the render is converged: block std <= ~1 LSB) on a grid inside each region, selected by colour
 and smoothness in the PNG itself.
 """
@@ -41,8 +45,22 @@ for name, ((x0, x1), (y0, y1), pred, tol) in REGIONS.items():
             m, s = blk.mean(0), blk.std(0)
             if s.max() < 1.3 and pred(m):
                 pts.append([x, y] + [round(float(c), 3) for c in m])
-    out[name] = {"tolerance_lsb_lo_hi": tol, "blocks_x_y_r_g_b": pts}
+    out[name] = {"tolerance_lsb_lo_hi": tol, "half_w": 4, "half_h": 4, "blocks_x_y_r_g_b": pts}
+    if name == "metal":
+        out[name]["max_abs_mean"] = 0.1          # no bias at all: mean over the blocks of (ours - png), per channel
     print(name, len(pts), "blocks")
+# horizon band: 15x3 blocks (the band is row-uniform locally) in columns whose row 200 shows the bare far ground
+pts = []
+FAR_GROUND = np.array([137.8, 156.1, 181.0])
+for x in list(range(15, 330, 35)) + list(range(1080, 1190, 35)):
+    if np.abs(im[199:202, x - 7:x + 8, :3].reshape(-1, 3).mean(0) - FAR_GROUND).max() > 0.4:
+        continue
+    for y in range(166, 202, 3):
+        blk = im[y - 1:y + 2, x - 7:x + 8, :3].reshape(-1, 3)
+        if blk.std(0).max() < 6.0:           # the band itself has a vertical gradient of ~5 LSB per row
+            pts.append([x, y] + [round(float(c), 3) for c in blk.mean(0)])
+out["horizon"] = {"tolerance_lsb_lo_hi": [-2.5, 2.5], "max_abs_mean": 0.4, "half_w": 7, "half_h": 1, "blocks_x_y_r_g_b": pts}
+print("horizon", len(pts), "blocks")
 json.dump({
     "source": "rtiow_part1_final.png (Druthyn/rtiow)", "width": 1200, "height": 800, "block": 9,
     "camera": {"look_from": [13, 2, 3], "look_at": [0, 0, 0], "v_up": [0, 1, 0], "v_fov": 20.0, "aspect_ratio": 1.5,

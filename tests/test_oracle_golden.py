@@ -52,12 +52,15 @@ def test_png_big_spheres(oracle, sampler):
     sc = oracle.Scene(s["center"], s["radius"], [0, 1, 2, 3], s["mat_kind"], s["mat_albedo"], s["mat_param"])
     cam = oracle.camera_new(**{k: v for k, v in g["camera"].items() if k != "cite"})
     ys = [b[1] for r in g["regions"].values() for b in r["blocks_x_y_r_g_b"]]
-    img, _, _ = oracle.render(sc, cam, g["width"], g["height"], spp=96, seed=7, rows=(min(ys) - 4, max(ys) + 5),
+    img, _, _ = oracle.render(sc, cam, g["width"], g["height"], spp=128, seed=7, rows=(min(ys) - 4, max(ys) + 5),
                               sampler=oracle.SAMPLER_DIRECT if sampler == "direct" else oracle.SAMPLER_REJECTION)
     for name, r in g["regions"].items():
         lo, hi = r["tolerance_lsb_lo_hi"]
-        d = np.array([img[y - 4:y + 5, x - 4:x + 5, :3].reshape(-1, 3).astype(float).mean(0) - np.array(c) for x, y, *c in r["blocks_x_y_r_g_b"]])
+        hw, hh = r["half_w"], r["half_h"]
+        d = np.array([img[y - hh:y + hh + 1, x - hw:x + hw + 1, :3].reshape(-1, 3).astype(float).mean(0) - np.array(c) for x, y, *c in r["blocks_x_y_r_g_b"]])
         assert len(d) >= 30 and lo <= d.min() and d.max() <= hi, f"{name}: block means differ from the reference PNG by {d.min():.2f} .. {d.max():.2f} LSB"
+        if "max_abs_mean" in r:
+            assert np.abs(d.mean(0)).max() <= r["max_abs_mean"], f"{name}: biased against the reference PNG by {d.mean(0)} LSB"
 
 
 def test_png_corner_pixels_exact(oracle):

@@ -121,8 +121,11 @@ def test_png_big_spheres_gpu(ctx, capi, prec):
     img, _ = render_gpu(ctx, capi, cam, width=g["width"], height=g["height"], spp=128, seed=7, precision=prec)
     for name, r in g["regions"].items():
         lo, hi = r["tolerance_lsb_lo_hi"]
-        d = np.array([img[y - 4:y + 5, x - 4:x + 5, :3].reshape(-1, 3).astype(float).mean(0) - np.array(c) for x, y, *c in r["blocks_x_y_r_g_b"]])
+        hw, hh = r["half_w"], r["half_h"]
+        d = np.array([img[y - hh:y + hh + 1, x - hw:x + hw + 1, :3].reshape(-1, 3).astype(float).mean(0) - np.array(c) for x, y, *c in r["blocks_x_y_r_g_b"]])
         assert lo <= d.min() and d.max() <= hi, f"{name}: block means differ from the reference PNG by {d.min():.2f} .. {d.max():.2f} LSB"
+        if "max_abs_mean" in r:
+            assert np.abs(d.mean(0)).max() <= r["max_abs_mean"], f"{name}: biased against the reference PNG by {d.mean(0)} LSB"
 
 
 def test_scene_too_large_for_shared_memory(ctx, capi, oracle, scene_factory):
