@@ -7,7 +7,9 @@
 
 A *step* is one full frame of the workload: BASELINE.json configs[1], the RTIOW Part 1 final scene
 (seeded random_scene, main.rs:59-102) at 1200x675, 500 spp, depth 50 — 405 M paths.  At N > 1 the same frame is
-split into interleaved row tiles, one rank per GPU, gathered with an NCCL all-gather ("strong" scaling).
+split into interleaved row tiles, one rank per GPU ("strong" scaling); the tiles reach rank 0 either fused into the epilogue
+(stores into rank 0's frame over NVLink, torch symmetric memory — default when available, cross-checked against the other
+path in the same run) or through tile buffers + an NCCL all-gather (--gather nccl).
 
   value     device-resident: scene already in HBM, tiles -> (all-gather) -> top-down frame left in HBM
   e2e       the reference-facing call with HOST buffers: scene upload (H2D) + render + frame to host (D2H)
@@ -67,6 +69,9 @@ def parse():
     ap.add_argument("--tile-rows", type=int, default=1)
     ap.add_argument("--cpu-sample-spp", type=int, default=0, help="spp of the bounded CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="auto", choices=["auto", "fused", "nccl"],
+                    help="N > 1: 'fused' = every rank's epilogue stores its pixels into rank 0's frame over NVLink (torch symmetric memory) and a "
+                         "device-side barrier follows; 'nccl' = tile buffers + NCCL all-gather + de-interleave; 'auto' = fused when available")
     a = ap.parse_args()
     name, w, h, spp, grid, mode = CONFIGS[a.config]
     a.workload = name if (a.width, a.height, a.spp) == (None, None, None) else f"{name} [overridden size]"
@@ -186,11 +191,40 @@ def run_ours(args, rank, local_rank, world):
     frame = torch.empty(W * H * 4, dtype=torch.uint8, device=dev)
     host_frame = torch.empty(W * H * 4, dtype=torch.uint8).pin_memory()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)        # > 126 MB L2
-    stream = torch.cuda.current_stream(dev)
+    # One dedicated stream for everything: the library's launches (it gets the raw handle), torch's fills and copies, NCCL's
+    # stream dependencies and the timing events.  (The legacy default stream has handle 0, which the C ABI reads as "use the
+    # context's own stream" — work there would not be ordered against torch's.)
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
     sp = stream.cuda_stream
+    assert sp != 0
     launches = [0]
 
-    def step_device(stats=False):
+    # N > 1, the gather.  Preferred: FUSED into the epilogue — rank 0's frame lives in symmetric memory (mapped into every rank's
+    # address space over NVLink), finalize_to_frame_kernel of each rank stores its rows straight into it, and a device-side barrier
+    # (signal pads, on the stream) tells rank 0 the frame is complete.  Fallback / cross-check: tile buffers + NCCL all-gather +
+    # de-interleave kernel, which is what north_star names.
+    fused, hdl, frame_sym, frame0_ptr, gather_note = False, None, None, 0, "single GPU"
+    if world > 1:
+        ok = 0
+        if args.gather in ("auto", "fused"):
+            try:
+                import torch.distributed._symmetric_memory as symm
+                frame_sym = symm.empty(W * H * 4, dtype=torch.uint8, device=dev)
+                hdl = symm.rendezvous(frame_sym, dist.group.WORLD)
+                frame0_ptr = int(hdl.buffer_ptrs[0])
+                ok = 1
+            except Exception as e:            # no P2P / symmetric-memory support on this box
+                gather_note = f"NCCL all-gather (symmetric memory unavailable: {type(e).__name__})"
+        t_ok = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+        fused = bool(t_ok.item())
+        if args.gather == "fused" and not fused:
+            raise SystemExit("bench.py: --gather fused requested but torch symmetric memory is not available")
+        if not fused and args.gather != "auto":
+            gather_note = "NCCL all-gather"
+
+    def step_nccl(stats=False):
         """tiles -> all-gather -> de-interleave, everything stays in HBM"""
         st = ctx.render_tiles_device(cam, prm, rank, world, tiles.data_ptr(), sp, want_stats=stats)
         launches[0] += 2
@@ -200,12 +234,39 @@ def run_ours(args, rank, local_rank, world):
             launches[0] += 1
         return st
 
+    def step_fused(stats=False):
+        """every rank's epilogue stores into rank 0's frame (peer memory), then a device-side barrier on the stream"""
+        st = ctx.render_to_frame_device(cam, prm, rank, world, frame0_ptr, sp, want_stats=stats)
+        launches[0] += 2
+        hdl.barrier(channel=0)
+        return st
+
+    if fused:                                 # cross-check once: the fused frame must equal the NCCL-gathered one, byte for byte
+        step_nccl(); step_fused(); torch.cuda.synchronize(dev)
+        same = torch.tensor([1 if (rank != 0 or torch.equal(frame_sym, frame)) else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        if not bool(same.item()):
+            if rank == 0:
+                a, b = frame_sym.view(H, W, 4), frame.view(H, W, 4)
+                bad_rows = (a != b).any(dim=2).any(dim=1).nonzero().flatten().tolist()
+                print(f"fused != nccl on {len(bad_rows)} rows, first {bad_rows[:12]}; frame0_ptr == local ptr: {frame0_ptr == frame_sym.data_ptr()}; "
+                      f"fused row sums {a[:4].sum(dim=(1, 2)).tolist()} nccl {b[:4].sum(dim=(1, 2)).tolist()}", file=sys.stderr)
+            raise SystemExit("bench.py: fused gather and NCCL all-gather disagree")
+        gather_note = "epilogue stores into rank 0's frame over NVLink (torch symmetric memory) + device-side barrier; verified byte-identical to tiles + NCCL all-gather + de-interleave"
+    step_device = step_fused if fused else step_nccl
+
     def step_e2e():
         """what a caller of the C ABI does per frame, from host buffers to host buffers"""
         ctx.upload_scene(**scene)                                                  # H2D: the scene SoA
         if world == 1:
             img, st = ctx.render(cam, prm, out=host_np)                            # D2H inside rtiow_render
             launches[0] += 2
+            return st
+        if fused:
+            st = step_fused(stats=True)
+            if rank == 0:
+                host_frame.copy_(frame_sym, non_blocking=True)
+            stream.synchronize()
             return st
         st = ctx.render_tiles_device(cam, prm, rank, world, tiles.data_ptr(), sp, want_stats=True)
         dist.all_gather_into_tensor(gathered, tiles)
@@ -298,7 +359,7 @@ def run_ours(args, rank, local_rank, world):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "width": W, "height": H, "spp": spp, "max_depth": WORKLOAD["max_depth"], "n_spheres": n_spheres,
                        "scene_seed": WORKLOAD["scene_seed"], "sample_seed": WORKLOAD["sample_seed"], "tile_rows": args.tile_rows,
-                       "parallelism": f"interleaved row tiles x{world}" + (", NCCL all-gather" if world > 1 else ""),
+                       "parallelism": f"interleaved row tiles x{world}" + (f", {gather_note}" if world > 1 else ""),
                        "l2": "256 MiB device buffer rewritten between timed steps (inside the timed region, ~0.1 ms)"},
             "clocks": clk,
             "e2e": {"value": paths / (e2e_ms * 1e-3) / 1e6, "unit": "Mpaths/s", "ms_per_step": e2e_ms,

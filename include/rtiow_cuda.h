@@ -137,6 +137,12 @@ int rtiow_tile_buffer_bytes(const rtiow_params* p, int world, size_t* out_bytes)
  * top-down order, on `stream` (a cudaStream_t, may be NULL).  Asynchronous unless stats != NULL. */
 int rtiow_render_tiles_device(rtiow_ctx* ctx, const rtiow_camera* cam, const rtiow_params* p, int rank, int world,
                               void* d_tiles, void* stream, rtiow_stats* stats);
+/* the same render with the gather FUSED into the epilogue: d_frame is the whole top-down frame (4*width*height bytes) in DEVICE
+ * memory — usually rank 0's buffer mapped into this process (CUDA IPC, torch symmetric memory) — and this rank's pixels are
+ * stored straight into their rows of it, over NVLink when it is remote.  Replaces tiles + all-gather + rtiow_deinterleave_device;
+ * the caller synchronises the ranks before rank 0 reads the frame. */
+int rtiow_render_to_frame_device(rtiow_ctx* ctx, const rtiow_camera* cam, const rtiow_params* p, int rank, int world,
+                                 void* d_frame, void* stream, rtiow_stats* stats);
 /* d_gathered = the G tile buffers concatenated in rank order (what an allgather leaves);
  * writes the top-down frame (4*width*height bytes) to DEVICE memory d_frame. */
 int rtiow_deinterleave_device(rtiow_ctx* ctx, const void* d_gathered, const rtiow_params* p, int world, void* d_frame,

@@ -27,7 +27,7 @@ PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint3
 SYMBOLS = [
     "rtiow_abi_version", "rtiow_last_error", "rtiow_device_count", "rtiow_ctx_create", "rtiow_ctx_create_on_device",
     "rtiow_ctx_destroy", "rtiow_scene_upload", "rtiow_camera_new", "rtiow_params_default", "rtiow_render", "rtiow_render_progressive",
-    "rtiow_tile_buffer_bytes", "rtiow_render_tiles_device", "rtiow_deinterleave_device", "rtiow_sphere_hit_batch",
+    "rtiow_tile_buffer_bytes", "rtiow_render_tiles_device", "rtiow_render_to_frame_device", "rtiow_deinterleave_device", "rtiow_sphere_hit_batch",
     "rtiow_hitlist_batch", "rtiow_scatter_batch", "rtiow_get_ray_batch", "rtiow_to_rgba_batch", "rtiow_reflect_batch",
     "rtiow_refract_batch", "rtiow_ray_color_batch", "rtiow_sampler_batch", "rtiow_fp32_peak_probe", "rtiow_flush_l2",
     "rtiow_random_scene",
@@ -110,6 +110,7 @@ def _declare(L):
         "rtiow_render_progressive": (C.c_int, [P, C.POINTER(Camera), C.POINTER(Params), C.c_uint32, PROGRESS_FN, P, P, C.POINTER(Stats)]),
         "rtiow_tile_buffer_bytes": (C.c_int, [C.POINTER(Params), C.c_int, C.POINTER(C.c_size_t)]),
         "rtiow_render_tiles_device": (C.c_int, [P, C.POINTER(Camera), C.POINTER(Params), C.c_int, C.c_int, P, P, C.POINTER(Stats)]),
+        "rtiow_render_to_frame_device": (C.c_int, [P, C.POINTER(Camera), C.POINTER(Params), C.c_int, C.c_int, P, P, C.POINTER(Stats)]),
         "rtiow_deinterleave_device": (C.c_int, [P, P, C.POINTER(Params), C.c_int, P, P]),
         "rtiow_sphere_hit_batch": (C.c_int, [P, C.c_int, i64] + [P] * 11),
         "rtiow_hitlist_batch": (C.c_int, [P, C.c_int, i64, P, P, d] + [P] * 6),
@@ -259,6 +260,13 @@ class Context:
         st = Stats()
         _check(lib().rtiow_render_tiles_device(self._h, C.byref(cam), C.byref(params), rank, world, C.c_void_p(d_tiles_ptr),
                                                C.c_void_p(stream_ptr), C.byref(st) if want_stats else None))
+        return st.as_dict() if want_stats else None
+
+    def render_to_frame_device(self, cam, params, rank, world, d_frame_ptr: int, stream_ptr: int = 0, want_stats=False):
+        """this rank's rows stored straight into the whole frame at d_frame_ptr (may be another GPU's memory): gather fused into the epilogue"""
+        st = Stats()
+        _check(lib().rtiow_render_to_frame_device(self._h, C.byref(cam), C.byref(params), rank, world, C.c_void_p(d_frame_ptr),
+                                                  C.c_void_p(stream_ptr), C.byref(st) if want_stats else None))
         return st.as_dict() if want_stats else None
 
     def deinterleave_device(self, d_gathered_ptr: int, params, world, d_frame_ptr: int, stream_ptr: int = 0):

@@ -467,10 +467,12 @@ static double now_ms()
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-extern "C" int rtiow_render_tiles_device(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_params* p, int rank, int world, void* d_tiles,
-                                         void* stream, rtiow_stats* stats)
+// shared body of the two per-rank entry points: this rank's rows into a tile buffer (rank-local order), or — with `to_frame` —
+// straight into their top-down place in a whole frame that may live on another GPU (finalize_to_frame_kernel)
+static int render_rank(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_params* p, int rank, int world, void* dst, bool to_frame, void* stream,
+                       rtiow_stats* stats)
 {
-    if (!c || !cam || !d_tiles) return fail(RTIOW_ERR_INVALID_ARG, "NULL argument");
+    if (!c || !cam || !dst) return fail(RTIOW_ERR_INVALID_ARG, "NULL argument");
     int rc = check_params(p); if (rc) return rc;
     if (world < 1 || rank < 0 || rank >= world) return fail(RTIOW_ERR_INVALID_ARG, "bad rank/world");
     DeviceState& d = c->dev[0];
@@ -479,7 +481,8 @@ extern "C" int rtiow_render_tiles_device(rtiow_ctx* c, const rtiow_camera* cam, 
     const double t0 = now_ms();
     uint32_t launches = 0;
     if (stats) CU(cudaEventRecord(d.ev0, st));
-    rc = render_tiles(c, d, cam, p, (uint32_t)rank, (uint32_t)world, (uint32_t*)d_tiles, st, &launches); if (rc) return rc;
+    rc = render_tiles(c, d, cam, p, (uint32_t)rank, (uint32_t)world, to_frame ? nullptr : (uint32_t*)dst, st, &launches, to_frame ? (uint32_t*)dst : nullptr);
+    if (rc) return rc;
     if (stats) {
         CU(cudaEventRecord(d.ev1, st));
         CU(cudaMemcpyAsync(d.pinned_cnt, d.counters.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -492,6 +495,22 @@ extern "C" int rtiow_render_tiles_device(rtiow_ctx* c, const rtiow_camera* cam, 
         stats->kernel_launches = launches; stats->n_gpus = 1;
     }
     return RTIOW_OK;
+}
+
+extern "C" int rtiow_render_tiles_device(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_params* p, int rank, int world, void* d_tiles,
+                                         void* stream, rtiow_stats* stats)
+{
+    return render_rank(c, cam, p, rank, world, d_tiles, false, stream, stats);
+}
+
+// The gather fused into the epilogue, for one-process-per-GPU jobs: d_frame is the WHOLE top-down frame (4*width*height bytes),
+// typically rank 0's buffer mapped into this process (CUDA IPC / torch symmetric memory); this rank's pixels are quantised and
+// stored straight into their rows of it — over NVLink when the buffer is remote.  No tile buffer, no all-gather, no
+// de-interleave; the caller only needs a barrier before rank 0 reads the frame.
+extern "C" int rtiow_render_to_frame_device(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_params* p, int rank, int world, void* d_frame,
+                                            void* stream, rtiow_stats* stats)
+{
+    return render_rank(c, cam, p, rank, world, d_frame, true, stream, stats);
 }
 
 extern "C" int rtiow_deinterleave_device(rtiow_ctx* c, const void* d_gathered, const rtiow_params* p, int world, void* d_frame, void* stream)

@@ -94,6 +94,8 @@ extern "C" {
     pub fn rtiow_tile_buffer_bytes(p: *const rtiow_params, world: c_int, out_bytes: *mut usize) -> c_int;
     pub fn rtiow_render_tiles_device(ctx: *mut rtiow_ctx, cam: *const rtiow_camera, p: *const rtiow_params, rank: c_int, world: c_int,
                                      d_tiles: *mut c_void, stream: *mut c_void, stats: *mut rtiow_stats) -> c_int;
+    pub fn rtiow_render_to_frame_device(ctx: *mut rtiow_ctx, cam: *const rtiow_camera, p: *const rtiow_params, rank: c_int, world: c_int,
+                                        d_frame: *mut c_void, stream: *mut c_void, stats: *mut rtiow_stats) -> c_int;
     pub fn rtiow_deinterleave_device(ctx: *mut rtiow_ctx, d_gathered: *const c_void, p: *const rtiow_params, world: c_int,
                                      d_frame: *mut c_void, stream: *mut c_void) -> c_int;
     pub fn rtiow_sphere_hit_batch(ctx: *mut rtiow_ctx, precision: c_int, n: i64, center: *const f64, radius: *const f64, orig: *const f64,

@@ -135,6 +135,7 @@ def test_invalid_arguments_do_not_crash(capi):
     assert L.rtiow_render_progressive(None, None, None, 4, capi.PROGRESS_FN(0), None, None, None) == capi.ERR_INVALID_ARG
     assert L.rtiow_camera_new(None, None, None, 1.0, 1.0, 1.0, 1.0, None) == capi.ERR_INVALID_ARG
     assert L.rtiow_tile_buffer_bytes(None, 1, None) == capi.ERR_INVALID_ARG
+    assert L.rtiow_render_to_frame_device(None, None, None, 0, 1, None, None, None) == capi.ERR_INVALID_ARG
     n = C.c_size_t(0)
     for bad in (dict(width=1), dict(height=0), dict(spp=0), dict(tile_rows=0), dict(precision=7), dict(t_min=-1.0)):
         p = capi.default_params(**bad)

@@ -185,7 +185,8 @@ def test_progressive_passes_are_prefixes_of_the_frame(ctx_final, capi, prec):
 @pytest.mark.parametrize("W,H,spp", [(1200, 675, 2), (400, 225, 10), (201, 133, 3)])
 def test_tile_partition_invariance(ctx_final, capi, W, H, spp):
     """N-GPU image == 1-GPU image, bit for bit: ranks are emulated one after another on this GPU through the
-    per-rank entry points the torchrun path uses (rtiow_render_tiles_device + rtiow_deinterleave_device)."""
+    per-rank entry points the torchrun path uses (rtiow_render_tiles_device + rtiow_deinterleave_device, and
+    rtiow_render_to_frame_device, whose epilogue stores into the whole frame)."""
     import torch
     cam = final_camera(capi, W / H)
     base, _ = ctx_final.render(cam, capi.default_params(width=W, height=H, spp=spp, seed=4))
@@ -203,6 +204,11 @@ def test_tile_partition_invariance(ctx_final, capi, W, H, spp):
         torch.cuda.synchronize()
         got = frame.cpu().numpy().reshape(H, W, 4)
         assert np.array_equal(got, base), f"world={world} tile_rows={tile_rows}: image differs from the single-GPU image"
+        # the gather fused into the epilogue (rtiow_render_to_frame_device): every rank stores straight into the whole frame
+        frame2 = torch.zeros(H * W * 4, dtype=torch.uint8, device="cuda")
+        rays2 = sum(ctx_final.render_to_frame_device(cam, prm, rank, world, frame2.data_ptr(), 0, want_stats=True)["rays_traced"] for rank in range(world))
+        torch.cuda.synchronize()
+        assert np.array_equal(frame2.cpu().numpy().reshape(H, W, 4), base) and rays2 == rays, f"world={world} tile_rows={tile_rows}: fused gather differs"
 
 
 def test_full_size_properties_cfg2(ctx_final, capi, oracle, final_scene):
