@@ -201,9 +201,12 @@ __device__ __forceinline__ bool assign_work(const RenderArgs<T>& a, WorkCursor& 
                 wc.cce = wc.cc + __shfl_sync(RT_FULL, take, 0); if (wc.cce > a.n_chunks) wc.cce = a.n_chunks;
                 if (wc.cc >= a.n_chunks) { wc.exhausted = true; break; }
             }
+            // chunks walk the frame BOTTOM-UP, like the reference's row index j (main.rs:122,132): the top rows come last, and
+            // in these scenes they are sky — one-ray paths — so the frame does not end on freshly started 50-bounce paths
             const unsigned long long c = wc.cc++;
-            wc.c_lp = (uint32_t)(c / a.chunks_per_pixel);
-            const uint32_t part = (uint32_t)(c - (unsigned long long)wc.c_lp * a.chunks_per_pixel);
+            const uint32_t pix = (uint32_t)(c / a.chunks_per_pixel);
+            const uint32_t part = (uint32_t)(c - (unsigned long long)pix * a.chunks_per_pixel);
+            wc.c_lp = a.local_rows * a.width - 1u - pix;
             wc.cs = part * a.chunk_samples; wc.ce = min(wc.cs + a.chunk_samples, a.spp);
             const uint32_t lr = wc.c_lp / a.width;
             wc.c_x = wc.c_lp - lr * a.width;
