@@ -245,13 +245,16 @@ def run_ours(args, rank, local_rank, world):
         step_nccl(); step_fused(); torch.cuda.synchronize(dev)
         same = torch.tensor([1 if (rank != 0 or torch.equal(frame_sym, frame)) else 0], dtype=torch.int32, device=dev)
         dist.all_reduce(same, op=dist.ReduceOp.MIN)
-        if not bool(same.item()):
+        if not bool(same.item()):             # never seen; if it happens the timed path is the one north_star names
             if rank == 0:
                 a, b = frame_sym.view(H, W, 4), frame.view(H, W, 4)
                 bad_rows = (a != b).any(dim=2).any(dim=1).nonzero().flatten().tolist()
-                print(f"fused != nccl on {len(bad_rows)} rows, first {bad_rows[:12]}; frame0_ptr == local ptr: {frame0_ptr == frame_sym.data_ptr()}; "
-                      f"fused row sums {a[:4].sum(dim=(1, 2)).tolist()} nccl {b[:4].sum(dim=(1, 2)).tolist()}", file=sys.stderr)
-            raise SystemExit("bench.py: fused gather and NCCL all-gather disagree")
+                print(f"bench.py: fused gather != NCCL all-gather on {len(bad_rows)} rows (first {bad_rows[:8]}): falling back to NCCL", file=sys.stderr)
+            if args.gather == "fused":
+                raise SystemExit("bench.py: fused gather and NCCL all-gather disagree")
+            fused = False
+            gather_note = "NCCL all-gather (the fused gather failed its cross-check on this box)"
+    if fused:
         gather_note = "epilogue stores into rank 0's frame over NVLink (torch symmetric memory) + device-side barrier; verified byte-identical to tiles + NCCL all-gather + de-interleave"
     step_device = step_fused if fused else step_nccl
 
