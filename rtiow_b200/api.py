@@ -106,3 +106,12 @@ def render(cam: capi.Camera, world: HittableList, params: capi.Params, n_gpus: i
         ctx.upload_scene(**world.to_arrays())
         img, _ = ctx.render(cam, params)
     return img
+
+
+def render_progressive(cam: capi.Camera, world: HittableList, params: capi.Params, n_passes: int, on_pass=None, n_gpus: int = 1):
+    """render() in n_passes slices of the samples; on_pass(pass_1based, n_passes, spp_done, rgba[H,W,4]) after each — the role of
+    the reference's progress bar and preview window (main.rs:120-124,151-171).  Final frame bit-identical to render()'s."""
+    with capi.Context(n_gpus) as ctx:
+        ctx.upload_scene(**world.to_arrays())
+        img, _ = ctx.render_progressive(cam, params, n_passes, on_pass)
+    return img
