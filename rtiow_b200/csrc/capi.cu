@@ -240,7 +240,7 @@ extern "C" int rtiow_scene_upload(rtiow_ctx* c, const rtiow_spheres* s, const rt
         UP(d.sph, sph, n, float4); UP(d.sphd, sphd, n, double4); UP(d.mat, mat, n, float4); UP(d.matd, matd, n, double4); UP(d.kind, kind, n, uint8_t);
 #undef UP
         CU(cudaStreamSynchronize(d.stream));
-        d.scene.table = d.table.p; d.scene.small = d.small.p; d.scene.small_idx = d.small_idx.p; d.scene.np = np;
+        d.scene.table = d.table.p; d.scene.small = d.small.p; d.scene.small_idx = d.small_idx.p; d.scene.np = np; d.scene.n_rec = (ns + 3) / 4;
         d.scene.filter_R2 = R2f; d.scene.filter_sigma = (float)(16.0 * 5.9604644775390625e-08 * std::max(rmax, 1e-3));
         d.scene.big = d.big.p; d.scene.big_idx = d.big_idx.p; d.scene.nb = nb;
         d.scene.sph = d.sph.p; d.scene.sphd = d.sphd.p; d.scene.mat = d.mat.p; d.scene.matd = d.matd.p; d.scene.kind = d.kind.p; d.scene.n = n;

@@ -23,7 +23,8 @@ struct SceneDev {
     const float* table;     // filter table, RT_TABLE_FLOATS(np) floats
     const float4* small;
     const int* small_idx;
-    int np;
+    int np;                 // small spheres incl. padding: a multiple of 32
+    int n_rec;              // 4-sphere records that hold real small spheres: ceil(ns / 4) <= np / 4
     float filter_R2;        // R^2: squared radius of the sphere around the coordinate origin that bounds every small sphere
     float filter_sigma;     // 16 u max|r|: per unit of |origin|_1, how far outside the R-sphere the filter's line point is put
     const double4* big;
@@ -166,21 +167,49 @@ __device__ __forceinline__ unsigned filter_word(const float4* __restrict__ rec, 
     return m;
 }
 
+// The last, partial word of the table: only its n_rec (1..7) records that hold real spheres are filtered (the final scene's
+// 529 small spheres are 16 words + 5 records: filtering the 3 all-padding records would be 2 % of the scan for nothing).
+__device__ __noinline__ unsigned filter_tail(const float4* __restrict__ rec, int n_rec, FilterRay f)
+{
+    unsigned m = 0;
+    float4 ncx = rec[0], ncy = rec[1], ncz = rec[2], nkk = rec[3];
+#pragma unroll 1
+    for (int q = 0; q < n_rec; ++q, rec += 4) {
+        const float4 cx = ncx, cy = ncy, cz = ncz, kk = nkk;
+        ncx = rec[4]; ncy = rec[5]; ncz = rec[6]; nkk = rec[7];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float2 X = h ? make_float2(cx.z, cx.w) : make_float2(cx.x, cx.y);
+            const float2 Y = h ? make_float2(cy.z, cy.w) : make_float2(cy.x, cy.y);
+            const float2 Z = h ? make_float2(cz.z, cz.w) : make_float2(cz.x, cz.y);
+            const float2 K = h ? make_float2(kk.z, kk.w) : make_float2(kk.x, kk.y);
+            const float2 hb = ffma2(X, bc2(f.DX), ffma2(Y, bc2(f.DY), ffma2(Z, bc2(f.DZ), bc2(f.NPD))));
+            const float2 C = ffma2(X, bc2(f.M2PX), ffma2(Y, bc2(f.M2PY), ffma2(Z, bc2(f.M2PZ), K)));
+            const float2 disc = ffma2(hb, hb, neg2(C));
+            m = __funnelshift_l(__float_as_uint(disc.x), m, 1);
+            m = __funnelshift_l(__float_as_uint(disc.y), m, 1);
+        }
+    }
+    const int absent = 32 - 4 * n_rec;                       // spheres of the word that were not filtered: marked "not passed"
+    return (m << absent) | ((1u << absent) - 1u);
+}
+
 template <bool kSmem>
-__device__ __forceinline__ void scan_small(const float* __restrict__ table, int np, float R2, float sigma_per_len, const float4* __restrict__ small,
+__device__ __forceinline__ void scan_small(const float* __restrict__ table, int n_rec, float R2, float sigma_per_len, const float4* __restrict__ small,
                                            V3<float> o, V3<float> dhat, float inv_a, float t_min, int self_pos, V3<float> self_n,
                                            uint16_t* cand, int cand_stride, float* t_best, int* p_best)
 {
-    const int n_words = np >> 5;
+    const int n_words = n_rec >> 3, n_tail = n_rec & 7;          // whole 32-sphere words; records of the partial last word
     int pb = *p_best; float tb = *t_best;
     // the sphere the ray starts on is tested on its own, independently of the filter
     if (self_pos >= 0) candidate_self<float>(dhat, inv_a, t_min, self_n, small[self_pos].w, self_pos, &tb, &pb);
-    if (n_words == 0) { *p_best = pb; *t_best = tb; return; }
+    if (n_rec == 0) { *p_best = pb; *t_best = tb; return; }
 
     const FilterRay f = make_filter_ray(o, dhat, inv_a, R2, sigma_per_len);
     const float4* rec = reinterpret_cast<const float4*>(table);
     float4 ncx = rec[0], ncy = rec[1], ncz = rec[2], nkk = rec[3];
-    for (int w0 = 0; w0 < n_words; w0 += RT_SEG_WORDS) {
+    int w0 = 0;
+    do {
         const int w1 = min(w0 + RT_SEG_WORDS, n_words);
         int nc = 0;
         for (int w = w0; w < w1; ++w, rec += 32) {
@@ -193,6 +222,15 @@ __device__ __forceinline__ void scan_small(const float* __restrict__ table, int 
                 else if (p != self_pos) { const float4 s = small[p]; candidate<float, true>(o, dhat, inv_a, t_min, mk(s.x, s.y, s.z), s.w, p, &tb, &pb); }
             }
         }
+        if (w1 == n_words && n_tail) {                                   // the partial word: survivors go straight to the precise test
+            unsigned c = ~filter_tail(reinterpret_cast<const float4*>(table) + (size_t)n_words * 32, n_tail, f);
+            while (c) {
+                const int k = __clz(c);
+                c &= ~(0x80000000u >> k);
+                const int p = (n_words << 5) + k;
+                if (p != self_pos) { const float4 s = small[p]; candidate<float, true>(o, dhat, inv_a, t_min, mk(s.x, s.y, s.z), s.w, p, &tb, &pb); }
+            }
+        }
         const int nmax = __reduce_max_sync(RT_FULL, nc);
         for (int k = 0; k < nmax; ++k) {
             if (k < nc) {
@@ -200,7 +238,8 @@ __device__ __forceinline__ void scan_small(const float* __restrict__ table, int 
                 if (p != self_pos) { const float4 s = small[p]; candidate<float, true>(o, dhat, inv_a, t_min, mk(s.x, s.y, s.z), s.w, p, &tb, &pb); }
             }
         }
-    }
+        w0 = w1;
+    } while (w0 < n_words);
     *p_best = pb; *t_best = tb;
 }
 
@@ -215,7 +254,7 @@ __device__ __forceinline__ HitF closest_hit(const SceneDev& sc, const float* tab
     const float inv_a = 1.0f / length_squared(dhat);
     float tb = __int_as_float(0x7f800000);   // f64::INFINITY at main.rs:44
     int pb = -1;
-    scan_small<kSmem>(table, sc.np, sc.filter_R2, sc.filter_sigma, sc.small, o, dhat, inv_a, t_min, self_code, self_n, cand, cand_stride, &tb, &pb);
+    scan_small<kSmem>(table, sc.n_rec, sc.filter_R2, sc.filter_sigma, sc.small, o, dhat, inv_a, t_min, self_code, self_n, cand, cand_stride, &tb, &pb);
     HitF h; h.t = tb; h.idx = pb >= 0 ? sc.small_idx[pb] : -1; h.code = pb;
     if (sc.nb > 0) {
         const V3<double> od = mk<double>(o.x, o.y, o.z), dd = mk<double>(dhat.x, dhat.y, dhat.z);
