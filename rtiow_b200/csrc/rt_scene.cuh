@@ -243,6 +243,29 @@ __device__ __forceinline__ void scan_small(const float* __restrict__ table, int 
     *p_best = pb; *t_best = tb;
 }
 
+// The spheres too large for f32 (|oc|^2 - r^2 of sphere.rs:22 cancels: the r = 1000 ground, main.rs:64), tested in f64 against
+// the closest hit so far.  Not inlined: once per ray, and kept out of the scan's register allocation.
+__device__ __noinline__ HitF big_spheres_hit(const double4* __restrict__ big, const int* __restrict__ big_idx, int nb, V3<float> o, V3<float> dhat,
+                                             float t_min, int self_code, V3<float> self_n, HitF h)
+{
+    const V3<double> od = mk<double>(o.x, o.y, o.z), dd = mk<double>(dhat.x, dhat.y, dhat.z);
+    const double inv_ad = 2.0 - length_squared(dd);          // 1/a for a = 1 + e, |e| < 1e-6: exact to e^2
+    double tbd = (double)h.t; int ib = h.idx;
+    for (int b = 0; b < nb; ++b) {
+        const double4 s = big[b];
+        const int before = ib; const double tbefore = tbd;
+        if (self_code == -2 - b) {
+            V3<double> sn = mk<double>(self_n.x, self_n.y, self_n.z);
+            sn = sn * (1.0 / sqrt(length_squared(sn)));
+            candidate_self<double>(dd, inv_ad, (double)t_min, sn, s.w, big_idx[b], &tbd, &ib);
+        } else {
+            candidate<double, true>(od, dd, inv_ad, (double)t_min, mk(s.x, s.y, s.z), s.w, big_idx[b], &tbd, &ib);
+        }
+        if (ib != before || tbd != tbefore) { h.idx = ib; h.t = (float)tbd; h.code = -2 - b; }
+    }
+    return h;
+}
+
 // Closest hit of one ray against the whole scene: HittableList::hit (mod.rs:56-69).
 // float: packed filter over the small spheres + f64 test of the big ones; all lanes of the warp
 // must call together.  self_code / self_n identify the sphere the ray starts on (RT_SELF_NONE for
@@ -256,23 +279,7 @@ __device__ __forceinline__ HitF closest_hit(const SceneDev& sc, const float* tab
     int pb = -1;
     scan_small<kSmem>(table, sc.n_rec, sc.filter_R2, sc.filter_sigma, sc.small, o, dhat, inv_a, t_min, self_code, self_n, cand, cand_stride, &tb, &pb);
     HitF h; h.t = tb; h.idx = pb >= 0 ? sc.small_idx[pb] : -1; h.code = pb;
-    if (sc.nb > 0) {
-        const V3<double> od = mk<double>(o.x, o.y, o.z), dd = mk<double>(dhat.x, dhat.y, dhat.z);
-        const double inv_ad = 2.0 - length_squared(dd);          // 1/a for a = 1 + e, |e| < 1e-6: exact to e^2
-        double tbd = (double)h.t; int ib = h.idx;
-        for (int b = 0; b < sc.nb; ++b) {
-            const double4 s = sc.big[b];
-            const int before = ib; const double tbefore = tbd;
-            if (self_code == -2 - b) {
-                V3<double> sn = mk<double>(self_n.x, self_n.y, self_n.z);
-                sn = sn * (1.0 / sqrt(length_squared(sn)));
-                candidate_self<double>(dd, inv_ad, (double)t_min, sn, s.w, sc.big_idx[b], &tbd, &ib);
-            } else {
-                candidate<double, true>(od, dd, inv_ad, (double)t_min, mk(s.x, s.y, s.z), s.w, sc.big_idx[b], &tbd, &ib);
-            }
-            if (ib != before || tbd != tbefore) { h.idx = ib; h.t = (float)tbd; h.code = -2 - b; }
-        }
-    }
+    if (sc.nb > 0) h = big_spheres_hit(sc.big, sc.big_idx, sc.nb, o, dhat, t_min, self_code, self_n, h);
     return h;
 }
 
