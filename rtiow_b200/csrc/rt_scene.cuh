@@ -274,7 +274,7 @@ template <bool kSmem>
 __device__ __forceinline__ HitF closest_hit(const SceneDev& sc, const float* table, V3<float> o, V3<float> dhat, float t_min,
                                             int self_code, V3<float> self_n, uint16_t* cand, int cand_stride)
 {
-    const float inv_a = 1.0f / length_squared(dhat);
+    const float inv_a = 2.0f - length_squared(dhat);           // 1/a for a = 1 + e, |e| < 1e-6 (dhat is unit to rounding): exact to e^2, no MUFU.RCP
     float tb = __int_as_float(0x7f800000);   // f64::INFINITY at main.rs:44
     int pb = -1;
     scan_small<kSmem>(table, sc.n_rec, sc.filter_R2, sc.filter_sigma, sc.small, o, dhat, inv_a, t_min, self_code, self_n, cand, cand_stride, &tb, &pb);
