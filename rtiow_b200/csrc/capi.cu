@@ -389,7 +389,8 @@ static int launch_render(DeviceState& d, const rtiow_camera* cam, const rtiow_pa
     a.width = p->width; a.height = p->height; a.spp = sr.count; a.smp_begin = sr.begin; a.max_depth = p->max_depth; a.t_min = (T)p->t_min; a.key = philox_key(p->seed);
     a.inv_wm1 = (T)(1.0 / (double)(p->width - 1)); a.inv_hm1 = (T)(1.0 / (double)(p->height - 1));
     a.rank = rank; a.world = world; a.tile_rows = p->tile_rows; a.local_rows = rows_of_rank(p->height, p->tile_rows, world, rank);
-    a.chunk_samples = std::min<uint32_t>(sr.count, getenv("RTIOW_TUNE_CHUNK") ? (uint32_t)atoi(getenv("RTIOW_TUNE_CHUNK")) : 64u);
+    const char* tune_chunk = getenv("RTIOW_TUNE_CHUNK");                  // experiment knob (tools/, not a product switch)
+    a.chunk_samples = std::min<uint32_t>(sr.count, tune_chunk ? (uint32_t)std::max(1, atoi(tune_chunk)) : 64u);
     a.chunks_per_pixel = (sr.count + a.chunk_samples - 1) / a.chunk_samples;
     a.chunks_per_fetch = std::max<uint32_t>(1u, 256u / a.chunk_samples);
     const uint64_t n_lp = (uint64_t)a.local_rows * p->width;
