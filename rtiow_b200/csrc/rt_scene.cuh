@@ -169,14 +169,23 @@ __device__ __forceinline__ unsigned filter_word(const float4* __restrict__ rec, 
 
 // The last, partial word of the table: only its n_rec (1..7) records that hold real spheres are filtered (the final scene's
 // 529 small spheres are 16 words + 5 records: filtering the 3 all-padding records would be 2 % of the scan for nothing).
+__device__ __forceinline__ float4 ld_rec(const float4* p, unsigned saddr, int i, bool smem)
+{
+    if (!smem) return p[i];
+    float4 v;                                               // shared-window load: a non-inlined function only sees a generic pointer
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr + 16u * (unsigned)i));
+    return v;
+}
+template <bool kSmem>
 __device__ __noinline__ unsigned filter_tail(const float4* __restrict__ rec, int n_rec, FilterRay f)
 {
     unsigned m = 0;
-    float4 ncx = rec[0], ncy = rec[1], ncz = rec[2], nkk = rec[3];
+    unsigned sa = kSmem ? (unsigned)__cvta_generic_to_shared(rec) : 0u;
+    float4 ncx = ld_rec(rec, sa, 0, kSmem), ncy = ld_rec(rec, sa, 1, kSmem), ncz = ld_rec(rec, sa, 2, kSmem), nkk = ld_rec(rec, sa, 3, kSmem);
 #pragma unroll 1
-    for (int q = 0; q < n_rec; ++q, rec += 4) {
+    for (int q = 0; q < n_rec; ++q, rec += 4, sa += 64u) {
         const float4 cx = ncx, cy = ncy, cz = ncz, kk = nkk;
-        ncx = rec[4]; ncy = rec[5]; ncz = rec[6]; nkk = rec[7];
+        ncx = ld_rec(rec, sa, 4, kSmem); ncy = ld_rec(rec, sa, 5, kSmem); ncz = ld_rec(rec, sa, 6, kSmem); nkk = ld_rec(rec, sa, 7, kSmem);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const float2 X = h ? make_float2(cx.z, cx.w) : make_float2(cx.x, cx.y);
@@ -223,7 +232,7 @@ __device__ __forceinline__ void scan_small(const float* __restrict__ table, int 
             }
         }
         if (w1 == n_words && n_tail) {                                   // the partial word: survivors go straight to the precise test
-            unsigned c = ~filter_tail(reinterpret_cast<const float4*>(table) + (size_t)n_words * 32, n_tail, f);
+            unsigned c = ~filter_tail<kSmem>(reinterpret_cast<const float4*>(table) + (size_t)n_words * 32, n_tail, f);
             while (c) {
                 const int k = __clz(c);
                 c &= ~(0x80000000u >> k);
