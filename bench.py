@@ -368,7 +368,9 @@ def run_ours(args, rank, local_rank, world):
             "e2e": {"value": paths / (e2e_ms * 1e-3) / 1e6, "unit": "Mpaths/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": scene_bytes + 176 + 48, "d2h_bytes_per_step": W * H * 4 + 16},
             "gpu_launches": n_launch,
-            "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
+            "roofline": {"bound": "fp32", "bound_note": "FP32 CUDA-core pipe (north_star's roofline): the scan is 7 packed FFMA2 per sphere pair out of shared memory; "
+                                                        "HBM traffic is ~20 MB per 9.7 TFLOP launch and tensor cores do not apply (no contraction)",
+                         "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
                          "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (world == 1 and args.config == "cfg2" and (W, H, spp) == (1200, 675, 500)) else None, "traffic_unit": "bytes/launch (ncu)",
                          "kernel": "rt::render_kernel<float,true,256,3>" if n_spheres < 2500 else "rt::render_kernel<float,true,768,1>", "kernel_ms": kms, "flop_per_test": FLOP_PER_TEST,
                          "rays_per_path": rays_total / paths, "sphere_tests_per_launch": rays_total * n_spheres / world,
