@@ -42,5 +42,8 @@ def test_single_process_multi_gpu_matches_single_gpu(capi, final_scene):
         with capi.Context(g) as cg:
             cg.upload_scene(**final_scene[0])
             img, st = cg.render(cam, prm)
+            seen = []
+            imgp, stp = cg.render_progressive(cam, prm, 3, lambda k, n_, done, frame: seen.append(done) or False)
         assert np.array_equal(img, base), f"{g}-GPU image differs from the 1-GPU image"
         assert st["rays_traced"] == st1["rays_traced"] and st["n_gpus"] == g
+        assert np.array_equal(imgp, base) and seen == [3, 6, 10] and stp["rays_traced"] == st1["rays_traced"], f"{g}-GPU progressive render differs"

@@ -173,3 +173,20 @@ def test_product_never_touches_the_oracle():
     assert not offenders, offenders
     out = subprocess.run(["ldd", str(ROOT / "rtiow_b200" / "lib" / "librtiow_cuda.so")], capture_output=True, text=True).stdout
     assert "oracle" not in out
+
+
+def test_bench_reference_arm_and_configs():
+    """bench.py: every BASELINE configuration is selectable, and the reference arm (the CPU restatement, no GPU) prints one JSON
+    line of the bench contract with impl = reference"""
+    import json, subprocess, sys
+    root = Path(__file__).resolve().parent.parent
+    sys.path.insert(0, str(root))
+    import bench
+    assert set(bench.CONFIGS) == {"cfg1", "cfg2", "cfg3-lambertian", "cfg3-metal", "cfg3-dielectric", "cfg4", "cfg5"}
+    assert bench.CONFIGS["cfg2"][1:4] == (1200, 675, 500) and bench.CONFIGS["cfg5"][1:4] == (3840, 2160, 1024)
+    r = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--config", "cfg1", "--steps", "1", "--warmup", "0",
+                        "--cpu-sample-spp", "1"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["metric"] == "Mpaths/s" and d["value"] > 0 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0 and d["config"]["width"] == 400
