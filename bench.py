@@ -154,7 +154,7 @@ def run_reference(args, rank):
     dt = time.perf_counter() - t0
     v = W * H * spp * args.steps / dt / 1e6
     sample = f"{W}x{H} @ {spp} spp per step ({W * H * spp / 1e6:.2f} M paths) of the {args.spp} spp workload; rate is spp-independent"
-    print(json.dumps({
+    emit_json({
         "impl": "reference", "metric": "Mpaths/s", "value": v, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": {"workload": args.workload, "width": W, "height": H, "spp": args.spp,
@@ -162,7 +162,7 @@ def run_reference(args, rank):
         "cpu_baseline": {"value": v, "unit": "Mpaths/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "CPU restatement of main.rs:122-145 (f64, gcc -O2, OpenMP rows); NOT `cargo run --release`: no rustc in this image"}))
+        "note": "CPU restatement of main.rs:122-145 (f64, gcc -O2, OpenMP rows); NOT `cargo run --release`: no rustc in this image"})
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
@@ -379,10 +379,32 @@ def run_ours(args, rank, local_rank, world):
         }
         if cpu:
             out["cpu_baseline"] = cpu
-        print(json.dumps(out))
+        emit_json(out)
     if world > 1:
         dist.destroy_process_group()
     ctx.close()
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """ONE JSON line on stdout, whatever libraries print: fd 1 is pointed at stderr for the run (NCCL's version banner, torch
+    warnings and the like land there) and the result line goes to the original stdout through emit_json()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, line)
+    else:
+        os.write(_REAL_STDOUT, line)
 
 
 def main():
@@ -395,6 +417,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", "29517", __file__] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args, rank)
     else:
