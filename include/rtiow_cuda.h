@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RTIOW_ABI_VERSION 2
+#define RTIOW_ABI_VERSION 3
 
 typedef enum {
     RTIOW_OK = 0,
@@ -43,6 +43,13 @@ typedef enum { RTIOW_MAT_LAMBERTIAN = 0, RTIOW_MAT_METAL = 1, RTIOW_MAT_DIELECTR
 /* arithmetic the render runs in.  F32 is the product path; F64 restates the reference's f64
  * arithmetic on the GPU for parity triage (same kernels, real_t = double). */
 typedef enum { RTIOW_PRECISION_F32 = 0, RTIOW_PRECISION_F64 = 1 } rtiow_precision;
+
+/* Where the sphere FILTER of the F32 scan runs (HittableList::hit, shapes/mod.rs:56-69: every ray against every sphere).
+ * FP32: 7 packed FFMA2 per sphere pair on the CUDA cores.  TENSOR: the discriminant as a [rays x 11] x [11 x spheres]
+ * contraction on the tcgen05 tensor cores (fp16 hi/lo split, fp32 accumulate in TMEM).  Both are conservative filters in
+ * front of the SAME precise test, so hits, images and ray counts are identical bit for bit.  AUTO = TENSOR when the scene
+ * qualifies (its small spheres fit one CTA's shared memory), else FP32. */
+typedef enum { RTIOW_SCAN_AUTO = 0, RTIOW_SCAN_FP32 = 1, RTIOW_SCAN_TENSOR = 2 } rtiow_scan_backend;
 
 /* HittableList of Sphere (shapes/mod.rs:52, shapes/sphere.rs:9-13) as a structure of arrays,
  * in LIST ORDER (order decides exact-tie hits: later index wins, sphere.rs:29,31 + mod.rs:61-66).
@@ -91,6 +98,8 @@ typedef struct {
     uint64_t h2d_bytes, d2h_bytes;
     uint32_t kernel_launches;
     uint32_t n_gpus;
+    uint32_t scan_backend;        /* rtiow_scan_backend the render launch used: RTIOW_SCAN_FP32 or RTIOW_SCAN_TENSOR */
+    uint32_t reserved;
 } rtiow_stats;
 
 typedef struct rtiow_ctx rtiow_ctx;
@@ -105,6 +114,9 @@ int  rtiow_ctx_create(int n_gpus, rtiow_ctx** out);
 /* One process per GPU (torchrun / MPI style): this ctx drives `device` only. */
 int  rtiow_ctx_create_on_device(int device, rtiow_ctx** out);
 void rtiow_ctx_destroy(rtiow_ctx* ctx);
+/* Select the filter backend of every later F32 call on this ctx (render and unit-level batches).  RTIOW_SCAN_TENSOR on a
+ * scene that does not qualify makes those calls return RTIOW_ERR_UNSUPPORTED (never a silent fallback). */
+int  rtiow_ctx_set_scan_backend(rtiow_ctx* ctx, int backend);
 
 /* Replaces building `world` for the GPU (main.rs:62-99 push calls): validates, converts to the
  * device SoA and uploads to every device of the ctx.  May be called again to replace the scene. */
@@ -178,6 +190,12 @@ int rtiow_refract_batch(rtiow_ctx* ctx, int precision, int64_t n, const double* 
 int rtiow_ray_color_batch(rtiow_ctx* ctx, int precision, int64_t n, const double* orig, const double* dir,
                           const uint32_t* pixel, const uint32_t* sample, uint64_t seed, int32_t max_depth, double t_min,
                           double* color, uint64_t* rays);
+/* the same, also recording every ray of every path: trace_index[i][k] = list index hit by the k-th ray of path i (-1: miss
+ * or no such ray), trace_ray[i][k] = (origin, unit direction) of that ray; both [n][max_depth], either may be NULL.  The
+ * parity tests use it to compare GPU and oracle paths ray by ray. */
+int rtiow_ray_color_trace_batch(rtiow_ctx* ctx, int precision, int64_t n, const double* orig, const double* dir,
+                                const uint32_t* pixel, const uint32_t* sample, uint64_t seed, int32_t max_depth, double t_min,
+                                double* color, uint64_t* rays, int32_t* trace_index, double* trace_ray);
 /* the sampler mapping itself: Philox4x32-10 block (seed; pixel, sample, bounce) -> 4 uniforms, the
  * lens-disk sample, the unit vector and the in-unit-sphere vector derived from them.  out: [n][12] */
 int rtiow_sampler_batch(rtiow_ctx* ctx, int precision, int64_t n, const uint32_t* pixel, const uint32_t* sample,

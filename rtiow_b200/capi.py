@@ -16,7 +16,8 @@ from . import build as _build
 OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_NCCL, ERR_NO_DEVICE, ERR_NOMEM, ERR_CANCELLED = 0, -1, -2, -3, -4, -5, -6, -7
 MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC = 0, 1, 2
 F32, F64 = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
+SCAN_AUTO, SCAN_FP32, SCAN_TENSOR = 0, 1, 2
 
 _STATUS = {OK: "OK", ERR_INVALID_ARG: "INVALID_ARG", ERR_UNSUPPORTED: "UNSUPPORTED", ERR_CUDA: "CUDA", ERR_NCCL: "NCCL",
            ERR_NO_DEVICE: "NO_DEVICE", ERR_NOMEM: "NOMEM", ERR_CANCELLED: "CANCELLED"}
@@ -26,10 +27,10 @@ PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint3
 # every symbol include/rtiow_cuda.h declares (tests check the .so exports exactly these)
 SYMBOLS = [
     "rtiow_abi_version", "rtiow_last_error", "rtiow_device_count", "rtiow_ctx_create", "rtiow_ctx_create_on_device",
-    "rtiow_ctx_destroy", "rtiow_scene_upload", "rtiow_camera_new", "rtiow_params_default", "rtiow_render", "rtiow_render_progressive",
+    "rtiow_ctx_destroy", "rtiow_ctx_set_scan_backend", "rtiow_scene_upload", "rtiow_camera_new", "rtiow_params_default", "rtiow_render", "rtiow_render_progressive",
     "rtiow_tile_buffer_bytes", "rtiow_render_tiles_device", "rtiow_render_to_frame_device", "rtiow_deinterleave_device", "rtiow_sphere_hit_batch",
     "rtiow_hitlist_batch", "rtiow_scatter_batch", "rtiow_get_ray_batch", "rtiow_to_rgba_batch", "rtiow_reflect_batch",
-    "rtiow_refract_batch", "rtiow_ray_color_batch", "rtiow_sampler_batch", "rtiow_fp32_peak_probe", "rtiow_flush_l2",
+    "rtiow_refract_batch", "rtiow_ray_color_batch", "rtiow_ray_color_trace_batch", "rtiow_sampler_batch", "rtiow_fp32_peak_probe", "rtiow_flush_l2",
     "rtiow_random_scene",
 ]
 
@@ -64,7 +65,7 @@ class Params(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("kernel_ms", C.c_double), ("total_ms", C.c_double), ("paths", C.c_uint64), ("rays_traced", C.c_uint64),
                 ("sphere_tests", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-                ("kernel_launches", C.c_uint32), ("n_gpus", C.c_uint32)]
+                ("kernel_launches", C.c_uint32), ("n_gpus", C.c_uint32), ("scan_backend", C.c_uint32), ("reserved", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -103,6 +104,7 @@ def _declare(L):
         "rtiow_ctx_create": (C.c_int, [C.c_int, C.POINTER(P)]),
         "rtiow_ctx_create_on_device": (C.c_int, [C.c_int, C.POINTER(P)]),
         "rtiow_ctx_destroy": (None, [P]),
+        "rtiow_ctx_set_scan_backend": (C.c_int, [P, C.c_int]),
         "rtiow_scene_upload": (C.c_int, [P, C.POINTER(Spheres), C.POINTER(Materials)]),
         "rtiow_camera_new": (C.c_int, [P, P, P, d, d, d, d, C.POINTER(Camera)]),
         "rtiow_params_default": (None, [C.POINTER(Params)]),
@@ -120,6 +122,7 @@ def _declare(L):
         "rtiow_reflect_batch": (C.c_int, [P, C.c_int, i64, P, P, P]),
         "rtiow_refract_batch": (C.c_int, [P, C.c_int, i64, P, P, P, P]),
         "rtiow_ray_color_batch": (C.c_int, [P, C.c_int, i64, P, P, P, P, u64, i32, d, P, P]),
+        "rtiow_ray_color_trace_batch": (C.c_int, [P, C.c_int, i64, P, P, P, P, u64, i32, d, P, P, P, P]),
         "rtiow_sampler_batch": (C.c_int, [P, C.c_int, i64, P, P, P, u64, P]),
         "rtiow_fp32_peak_probe": (C.c_int, [P, C.c_int, d, C.POINTER(d), C.POINTER(d)]),
         "rtiow_flush_l2": (C.c_int, [P]),
@@ -196,6 +199,10 @@ class Context:
         if getattr(self, "_h", None):
             lib().rtiow_ctx_destroy(self._h)
             self._h = None
+
+    def set_scan_backend(self, backend: int):
+        """SCAN_AUTO / SCAN_FP32 (FFMA2 filter on the CUDA cores) / SCAN_TENSOR (tcgen05 filter): same hits, same images."""
+        _check(lib().rtiow_ctx_set_scan_backend(self._h, backend))
 
     def __del__(self):
         try:
@@ -330,6 +337,16 @@ class Context:
         _check(lib().rtiow_ray_color_batch(self._h, precision, n, _p(orig), _p(direction), _p(pixel), _p(sample), seed, max_depth,
                                            t_min, _p(col), _p(rays)))
         return dict(color=col, rays=rays)
+
+    def ray_color_trace_batch(self, orig, direction, pixel, sample, seed, max_depth=50, t_min=1e-4, precision=F32):
+        """ray_color_batch + every ray of every path: index[n][max_depth] (list index hit, -1 = miss / no ray), ray[n][max_depth][6]"""
+        orig, direction = _f64(orig, (-1, 3)), _f64(direction, (-1, 3)); n = len(orig)
+        pixel = np.ascontiguousarray(pixel, np.uint32); sample = np.ascontiguousarray(sample, np.uint32)
+        col = np.zeros((n, 3)); rays = np.zeros(n, np.uint64)
+        idx = np.full((n, max_depth), -1, np.int32); ray = np.zeros((n, max_depth, 6))
+        _check(lib().rtiow_ray_color_trace_batch(self._h, precision, n, _p(orig), _p(direction), _p(pixel), _p(sample), seed, max_depth,
+                                                 t_min, _p(col), _p(rays), _p(idx), _p(ray)))
+        return dict(color=col, rays=rays, index=idx, ray=ray)
 
     def sampler_batch(self, pixel, sample, bounce, seed, precision=F32):
         pixel = np.ascontiguousarray(pixel, np.uint32); sample = np.ascontiguousarray(sample, np.uint32)

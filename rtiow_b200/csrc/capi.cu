@@ -31,7 +31,10 @@ static int fail(int code, const char* fmt, ...)
 #define CU(call)                                                                                         \
     do {                                                                                                 \
         cudaError_t e_ = (call);                                                                         \
-        if (e_ != cudaSuccess) return fail(RTIOW_ERR_CUDA, "%s -> %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+        if (e_ != cudaSuccess) {                                                                         \
+            cudaGetLastError();                                                                          \
+            return fail(e_ == cudaErrorMemoryAllocation ? RTIOW_ERR_NOMEM : RTIOW_ERR_CUDA, "%s -> %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+        }                                                                                                \
     } while (0)
 
 extern "C" int rtiow_abi_version(void) { return RTIOW_ABI_VERSION; }
@@ -71,6 +74,7 @@ struct DeviceState {
     // scene
     DevBuf<float> table; DevBuf<float4> small; DevBuf<int> small_idx; DevBuf<double4> big; DevBuf<int> big_idx;
     DevBuf<float4> sph; DevBuf<double4> sphd; DevBuf<float4> mat; DevBuf<double4> matd; DevBuf<uint8_t> kind;
+    DevBuf<unsigned char> ubimg;                       // tensor-core filter: the spheres' fp16 hi/lo feature image (rt_umma.cuh)
     SceneDev scene{};
     bool has_scene = false;
     // frame
@@ -80,10 +84,12 @@ struct DeviceState {
     unsigned long long* pinned_cnt = nullptr;
     // measurement
     DevBuf<uint4> flush; DevBuf<float> probe;
+    int last_backend = RTIOW_SCAN_FP32;                // which filter the last render launch used (rtiow_stats.scan_backend)
 };
 
 struct rtiow_ctx {
     std::vector<DeviceState> dev;
+    int scan_backend = RTIOW_SCAN_AUTO;  // rtiow_ctx_set_scan_backend
     size_t scene_bytes = 0;
     bool peer_ok = true;                 // every device can store into device 0's memory (NVLink P2P): fused epilogue + gather
 };
@@ -93,7 +99,8 @@ static int init_device(DeviceState& d, int device)
     d.device = device;
     CU(cudaSetDevice(device));
     cudaDeviceProp p; CU(cudaGetDeviceProperties(&p, device));
-    if (p.major < 10) return fail(RTIOW_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device, p.major, p.minor);
+    // arch-specific targets are not forward compatible: sm_100a code runs on compute capability 10.0 and nothing else
+    if (p.major != 10 || p.minor != 0) return fail(RTIOW_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, p.major, p.minor);
     d.sms = p.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&d.ev0)); CU(cudaEventCreate(&d.ev1)); CU(cudaEventCreateWithFlags(&d.ev_done, cudaEventDisableTiming));
@@ -141,6 +148,14 @@ extern "C" int rtiow_ctx_create(int n_gpus, rtiow_ctx** out)
 }
 extern "C" int rtiow_ctx_create_on_device(int device, rtiow_ctx** out) { return create_ctx(std::vector<int>{ device }, out); }
 
+extern "C" int rtiow_ctx_set_scan_backend(rtiow_ctx* c, int backend)
+{
+    if (!c) return fail(RTIOW_ERR_INVALID_ARG, "ctx is NULL");
+    if (backend != RTIOW_SCAN_AUTO && backend != RTIOW_SCAN_FP32 && backend != RTIOW_SCAN_TENSOR) return fail(RTIOW_ERR_INVALID_ARG, "unknown scan backend %d", backend);
+    c->scan_backend = backend;
+    return RTIOW_OK;
+}
+
 extern "C" void rtiow_ctx_destroy(rtiow_ctx* c)
 {
     if (!c) return;
@@ -148,7 +163,7 @@ extern "C" void rtiow_ctx_destroy(rtiow_ctx* c)
         cudaSetDevice(d.device);
         if (d.stream) cudaStreamSynchronize(d.stream);
         d.table.release(); d.small.release(); d.small_idx.release(); d.big.release(); d.big_idx.release();
-        d.sph.release(); d.sphd.release(); d.mat.release(); d.matd.release(); d.kind.release();
+        d.sph.release(); d.sphd.release(); d.mat.release(); d.matd.release(); d.kind.release(); d.ubimg.release();
         d.accum.release(); d.counters.release(); d.tiles.release(); d.gathered.release(); d.frame.release();
         d.flush.release(); d.probe.release();
         if (d.pinned) cudaFreeHost(d.pinned);
@@ -228,22 +243,62 @@ extern "C" int rtiow_scene_upload(rtiow_ctx* c, const rtiow_spheres* s, const rt
     }
     for (int k = 0; k < 4; ++k) table[(size_t)np * 4 + 12 + k] = 1e30f;        // the look-ahead record: never hit, never used
     std::vector<double4> big(nb); for (int b = 0; b < nb; ++b) big[b] = sphd[big_ids[b]];
+    // Tensor-core filter (rt_umma.cuh): per small sphere the 11 features of the bilinear discriminant, scaled by powers of
+    // two chosen from the bounding radius, split hi/lo in fp16, in the canonical K-major layout.  S_0 carries the slack that
+    // bounds the 3-product split and the fp32 accumulation (tools/probe_umma_filter.cu measures 1.15e-6 R^2; 1.5625e-5 R^2 here).
+    // Enabled when the image fits beside the candidate lists in one CTA's shared memory and the slack stays below the
+    // mean r^2 (a scene spread over a huge radius would pass every sphere near the line; the FP32 filter handles those).
+    std::vector<unsigned char> ubimg; int u_npad = 0; umma::FeatScale u_sc{ 1.0f, 1.0f, 1.0f, 1.0f };
+    {
+        using Shape = UmmaShape<RT_UMMA_GROUPS, RT_UMMA_CHUNK>;
+        const int npad = (ns + RT_UMMA_CHUNK - 1) / RT_UMMA_CHUNK * RT_UMMA_CHUNK;
+        const double Rp = std::exp2(std::ceil(std::log2(R)));
+        const double slack = 1.5625e-5 * R * R;
+        double mean_r2 = 0; for (int id : small_ids) mean_r2 += (double)sph[id].w * sph[id].w;
+        mean_r2 = ns ? mean_r2 / ns : 0.0;
+        if (ns > 0 && npad < 65536 && Shape::smem_bytes(npad) <= 227 * 1024 && Rp <= 8192.0 && slack <= mean_r2) {
+            u_npad = npad;
+            u_sc = umma::FeatScale{ (float)Rp, 1.0f, (float)(Rp * 0.5), (float)(1.0 / Rp) };
+            const size_t blk = RT_UMMA_B_BLOCK_BYTES(npad);
+            ubimg.assign(2 * blk, 0);
+            auto put = [&](int j, int k, double val) {
+                const float x = (float)val; const __half h = __float2half_rn(x); const __half l = __float2half_rn(x - __half2float(h));
+                memcpy(&ubimg[umma::b_offset(j, k)], &h, 2);
+                memcpy(&ubimg[blk + umma::b_offset(j, k)], &l, 2);
+            };
+            for (int j = 0; j < npad; ++j) {
+                if (j < ns) {                     // position j of `small` (list order); the f32 sphere the precise test sees
+                    const float4 v = sph[order[j]];
+                    const double x = v.x, y = v.y, z = v.z, r = v.w;
+                    put(j, 0, (r * r - (x * x + y * y + z * z) + slack) / u_sc.s0);
+                    put(j, 1, x / u_sc.s1); put(j, 2, y / u_sc.s1); put(j, 3, z / u_sc.s1);
+                    put(j, 4, x * x / u_sc.s4); put(j, 5, y * y / u_sc.s4); put(j, 6, z * z / u_sc.s4);
+                    put(j, 7, x * y / u_sc.s4); put(j, 8, x * z / u_sc.s4); put(j, 9, y * z / u_sc.s4);
+                } else {
+                    put(j, 0, -4.0 * Rp * Rp / u_sc.s0);              // padding: never passes, whatever the ray
+                }
+                put(j, 10, 1.0 / u_sc.s10);
+            }
+        }
+    }
     c->scene_bytes = 0;
     for (auto& d : c->dev) {
         CU(cudaSetDevice(d.device));
         CU(d.table.resize(table.size())); CU(d.small.resize(np)); CU(d.small_idx.resize(np)); CU(d.big.resize(nb)); CU(d.big_idx.resize(nb));
-        CU(d.sph.resize(n)); CU(d.sphd.resize(n)); CU(d.mat.resize(n)); CU(d.matd.resize(n)); CU(d.kind.resize(n));
+        CU(d.sph.resize(n)); CU(d.sphd.resize(n)); CU(d.mat.resize(n)); CU(d.matd.resize(n)); CU(d.kind.resize(n)); CU(d.ubimg.resize(ubimg.size()));
         size_t bytes = 0;
 #define UP(dst, src, cnt, type) do { if ((cnt) > 0) { CU(cudaMemcpyAsync(dst.p, src.data(), (size_t)(cnt) * sizeof(type), cudaMemcpyHostToDevice, d.stream)); bytes += (size_t)(cnt) * sizeof(type); } } while (0)
         UP(d.table, table, table.size(), float); UP(d.small, small, np, float4); UP(d.small_idx, small_idx, np, int);
         UP(d.big, big, nb, double4); UP(d.big_idx, big_ids, nb, int);
         UP(d.sph, sph, n, float4); UP(d.sphd, sphd, n, double4); UP(d.mat, mat, n, float4); UP(d.matd, matd, n, double4); UP(d.kind, kind, n, uint8_t);
+        UP(d.ubimg, ubimg, ubimg.size(), unsigned char);
 #undef UP
         CU(cudaStreamSynchronize(d.stream));
         d.scene.table = d.table.p; d.scene.small = d.small.p; d.scene.small_idx = d.small_idx.p; d.scene.np = np; d.scene.n_rec = (ns + 3) / 4;
         d.scene.filter_R2 = R2f; d.scene.filter_sigma = (float)(16.0 * 5.9604644775390625e-08 * std::max(rmax, 1e-3));
         d.scene.big = d.big.p; d.scene.big_idx = d.big_idx.p; d.scene.nb = nb;
         d.scene.sph = d.sph.p; d.scene.sphd = d.sphd.p; d.scene.mat = d.mat.p; d.scene.matd = d.matd.p; d.scene.kind = d.kind.p; d.scene.n = n;
+        d.scene.u_bimg = d.ubimg.p; d.scene.u_npad = u_npad; d.scene.u_sc = u_sc;
         d.has_scene = true;
         c->scene_bytes = bytes;
     }
@@ -326,7 +381,7 @@ static int check_params(const rtiow_params* p)
     if (p->width < 2 || p->height < 2) return fail(RTIOW_ERR_INVALID_ARG, "width and height must be >= 2 (jitter divides by W-1, H-1: main.rs:131-132)");
     if (p->spp == 0) return fail(RTIOW_ERR_INVALID_ARG, "spp must be >= 1");
     if ((uint64_t)p->width * p->height > 0xfffffff0ull) return fail(RTIOW_ERR_INVALID_ARG, "frame too large");
-    if (p->tile_rows == 0) return fail(RTIOW_ERR_INVALID_ARG, "tile_rows must be >= 1");
+    if (p->tile_rows == 0 || p->tile_rows > p->height) return fail(RTIOW_ERR_INVALID_ARG, "tile_rows must be in [1, height]");
     if (p->precision > RTIOW_PRECISION_F64) return fail(RTIOW_ERR_INVALID_ARG, "unknown precision");
     if (!(p->t_min >= 0.0)) return fail(RTIOW_ERR_INVALID_ARG, "t_min must be >= 0");
     return RTIOW_OK;
@@ -377,11 +432,22 @@ template <typename T> static void size_fetch(RenderArgs<T>& a, int grid, int thr
     const uint64_t cap = std::max<uint32_t>(1u, 256u / a.chunk_samples);
     a.chunks_per_fetch = (uint32_t)std::min<uint64_t>(cap, std::max<uint64_t>(1, want));
     a.guided_div = (uint32_t)std::max<uint64_t>(1, 2 * n_warps);
-    if (const char* t = getenv("RTIOW_TUNE_GUIDED")) a.guided_div = (uint32_t)std::max(1, atoi(t));   // experiment knob (tools/): 1 = off
+#ifdef RTIOW_TUNING                      // experiment builds only (tools/ab.sh): the product library reads no environment
+    if (const char* t = getenv("RTIOW_TUNE_GUIDED")) a.guided_div = (uint32_t)std::max(1, atoi(t));
+#endif
+}
+
+// which filter runs: the tensor-core one when the scene qualifies (rtiow_scene_upload) and the caller did not ask otherwise
+static bool use_tensor_scan(const rtiow_ctx* c, const DeviceState& d) { return d.scene.u_npad > 0 && c->scan_backend != RTIOW_SCAN_FP32; }
+static int check_scan_backend(const rtiow_ctx* c, const DeviceState& d)
+{
+    if (c->scan_backend == RTIOW_SCAN_TENSOR && d.scene.u_npad == 0)
+        return fail(RTIOW_ERR_UNSUPPORTED, "RTIOW_SCAN_TENSOR requested but the scene does not qualify for the tensor-core filter (too many / too widely spread small spheres)");
+    return RTIOW_OK;
 }
 
 template <typename T>
-static int launch_render(DeviceState& d, const rtiow_camera* cam, const rtiow_params* p, uint32_t rank, uint32_t world, uint32_t* d_tiles,
+static int launch_render(const rtiow_ctx* c, DeviceState& d, const rtiow_camera* cam, const rtiow_params* p, uint32_t rank, uint32_t world, uint32_t* d_tiles,
                          cudaStream_t st, uint32_t* launches, uint32_t* peer_frame, SampleRange sr)
 {
     RenderArgs<T> a;
@@ -389,8 +455,11 @@ static int launch_render(DeviceState& d, const rtiow_camera* cam, const rtiow_pa
     a.width = p->width; a.height = p->height; a.spp = sr.count; a.smp_begin = sr.begin; a.max_depth = p->max_depth; a.t_min = (T)p->t_min; a.key = philox_key(p->seed);
     a.inv_wm1 = (T)(1.0 / (double)(p->width - 1)); a.inv_hm1 = (T)(1.0 / (double)(p->height - 1));
     a.rank = rank; a.world = world; a.tile_rows = p->tile_rows; a.local_rows = rows_of_rank(p->height, p->tile_rows, world, rank);
-    const char* tune_chunk = getenv("RTIOW_TUNE_CHUNK");                  // experiment knob (tools/, not a product switch)
-    a.chunk_samples = std::min<uint32_t>(sr.count, tune_chunk ? (uint32_t)std::max(1, atoi(tune_chunk)) : 64u);
+    uint32_t chunk = 64u;
+#ifdef RTIOW_TUNING
+    if (const char* t = getenv("RTIOW_TUNE_CHUNK")) chunk = (uint32_t)std::max(1, atoi(t));
+#endif
+    a.chunk_samples = std::min<uint32_t>(sr.count, chunk);
     a.chunks_per_pixel = (sr.count + a.chunk_samples - 1) / a.chunk_samples;
     a.chunks_per_fetch = std::max<uint32_t>(1u, 256u / a.chunk_samples);
     const uint64_t n_lp = (uint64_t)a.local_rows * p->width;
@@ -402,14 +471,28 @@ static int launch_render(DeviceState& d, const rtiow_camera* cam, const rtiow_pa
     if (n_lp == 0) return RTIOW_OK;
     int grid = 0;
     if (sizeof(T) == 8) {
+        d.last_backend = RTIOW_SCAN_FP32;
         auto k = render_kernel<T, false, 256, 2>;
         int rc = prep_kernel(k, 0, 256, d.sms, &grid); if (rc) return rc;
         size_fetch(a, grid, 256);
         k<<<grid, 256, 0, st>>>(a);
+    } else if (sizeof(T) == 4 && use_tensor_scan(c, d)) {
+        // sphere filter on the tensor cores: one CTA per SM (it owns all of TMEM), G groups of 128 rays + G issuer warps
+        using Shape = UmmaShape<RT_UMMA_GROUPS, RT_UMMA_CHUNK>;
+        auto k = render_kernel_umma<RT_UMMA_GROUPS, RT_UMMA_CHUNK>;
+        const size_t sm = Shape::smem_bytes(d.scene.u_npad);
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        grid = d.sms;
+        size_fetch(a, grid, Shape::kRayThreads);
+        k<<<grid, Shape::kThreads, sm, st>>>(reinterpret_cast<const RenderArgs<float>&>(a));
+        d.last_backend = RTIOW_SCAN_TENSOR;
     } else {
         const ScanCfg cfg = pick_cfg(d.scene.np);
-        const char* tune = getenv("RTIOW_TUNE_MIN_CTAS");        // experiment knob (tools/, not a product switch)
-        const int min_ctas = tune ? atoi(tune) : 3;             // 3 CTAs x 256 threads x 80 registers fills the 64K-register file
+        int min_ctas = 3;                                       // 3 CTAs x 256 threads x 80 registers fills the 64K-register file
+#ifdef RTIOW_TUNING
+        if (const char* t = getenv("RTIOW_TUNE_MIN_CTAS")) min_ctas = atoi(t);
+#endif
+        d.last_backend = RTIOW_SCAN_FP32;
         if (cfg.variant == 0 && min_ctas == 3) {
             auto k = render_kernel<T, true, 256, 3>;
             int rc = prep_kernel(k, cfg.smem, 256, d.sms, &grid); if (rc) return rc;
@@ -459,8 +542,9 @@ static int render_tiles(const rtiow_ctx* c, DeviceState& d, const rtiow_camera* 
     if (!d.has_scene) return fail(RTIOW_ERR_INVALID_ARG, "no scene uploaded (call rtiow_scene_upload first)");
     CU(cudaSetDevice(d.device));
     const SampleRange sr = range ? *range : SampleRange{ 0u, p->spp };
-    return p->precision == RTIOW_PRECISION_F64 ? launch_render<double>(d, cam, p, rank, world, d_tiles, st, launches, peer_frame, sr)
-                                               : launch_render<float>(d, cam, p, rank, world, d_tiles, st, launches, peer_frame, sr);
+    if (p->precision != RTIOW_PRECISION_F64) { int rc = check_scan_backend(c, d); if (rc) return rc; }
+    return p->precision == RTIOW_PRECISION_F64 ? launch_render<double>(c, d, cam, p, rank, world, d_tiles, st, launches, peer_frame, sr)
+                                               : launch_render<float>(c, d, cam, p, rank, world, d_tiles, st, launches, peer_frame, sr);
 }
 
 static double now_ms()
@@ -493,7 +577,7 @@ static int render_rank(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_params
         stats->kernel_ms = ms; stats->total_ms = now_ms() - t0;
         stats->paths = (uint64_t)rows_of_rank(p->height, p->tile_rows, world, rank) * p->width * p->spp;
         stats->rays_traced = d.pinned_cnt[1]; stats->sphere_tests = stats->rays_traced * (uint64_t)d.scene.n;
-        stats->kernel_launches = launches; stats->n_gpus = 1;
+        stats->kernel_launches = launches; stats->n_gpus = 1; stats->scan_backend = (uint32_t)d.last_backend;
     }
     return RTIOW_OK;
 }
@@ -604,7 +688,7 @@ static int render_frame(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_param
         stats->paths = (uint64_t)p->width * p->height * sr.count;
         stats->rays_traced = rays; stats->sphere_tests = rays * (uint64_t)d0.scene.n;
         stats->h2d_bytes = sizeof(rtiow_camera) + sizeof(rtiow_params); stats->d2h_bytes = frame_bytes + 16;
-        stats->kernel_launches = launches; stats->n_gpus = world;
+        stats->kernel_launches = launches; stats->n_gpus = world; stats->scan_backend = (uint32_t)d0.last_backend;
     }
     return RTIOW_OK;
 }
@@ -636,7 +720,7 @@ extern "C" int rtiow_render_progressive(rtiow_ctx* c, const rtiow_camera* cam, c
         rc = render_frame(c, cam, p, SampleRange{ done, upto - done }, out_rgba, &st); if (rc) return rc;
         done = upto;
         total.kernel_ms += st.kernel_ms; total.paths += st.paths; total.rays_traced += st.rays_traced; total.sphere_tests += st.sphere_tests;
-        total.h2d_bytes += st.h2d_bytes; total.d2h_bytes += st.d2h_bytes; total.kernel_launches += st.kernel_launches; total.n_gpus = st.n_gpus;
+        total.h2d_bytes += st.h2d_bytes; total.d2h_bytes += st.d2h_bytes; total.kernel_launches += st.kernel_launches; total.n_gpus = st.n_gpus; total.scan_backend = st.scan_backend;
         if (on_pass && on_pass(user, k + 1, n_passes, done, out_rgba) != 0 && k + 1 < n_passes) {
             total.total_ms = now_ms() - t0;
             if (stats) *stats = total;
@@ -688,6 +772,7 @@ extern "C" int rtiow_sphere_hit_batch(rtiow_ctx* c, int precision, int64_t n, co
                                       double* normal, int32_t* front_face)
 {
     BATCH_PROLOGUE();
+    if (!center || !radius || !orig || !dir || !t_min || !t_max || !hit || !t || !p || !normal || !front_face) return fail(RTIOW_ERR_INVALID_ARG, "NULL array");
     if (n == 0) return RTIOW_OK;
     double *dc, *dr, *dor, *dd, *dtn, *dtx, *dt, *dp, *dn; int32_t *dh, *dff;
     CU(S.in(center, N3, &dc)); CU(S.in(radius, n, &dr)); CU(S.in(orig, N3, &dor)); CU(S.in(dir, N3, &dd)); CU(S.in(t_min, n, &dtn)); CU(S.in(t_max, n, &dtx));
@@ -705,6 +790,8 @@ extern "C" int rtiow_hitlist_batch(rtiow_ctx* c, int precision, int64_t n, const
 {
     BATCH_PROLOGUE();
     if (!d.has_scene) return fail(RTIOW_ERR_INVALID_ARG, "no scene uploaded");
+    if (!orig || !dir || !hit || !index || !t || !p || !normal || !front_face) return fail(RTIOW_ERR_INVALID_ARG, "NULL array");
+    if (precision == RTIOW_PRECISION_F32) { int rc = check_scan_backend(c, d); if (rc) return rc; }
     if (n == 0) return RTIOW_OK;
     SceneDev scene = d.scene;
     double *dor, *dd, *dt, *dp, *dn; int32_t *dh, *di, *dff;
@@ -712,10 +799,18 @@ extern "C" int rtiow_hitlist_batch(rtiow_ctx* c, int precision, int64_t n, const
     CU(S.out(n, &dh)); CU(S.out(n, &di)); CU(S.out(n, &dt)); CU(S.out(N3, &dp)); CU(S.out(N3, &dn)); CU(S.out(n, &dff));
     if (precision == RTIOW_PRECISION_F64) {
         hitlist_kernel<double, false, 256><<<grid, 256, 0, d.stream>>>(scene, n, dor, dd, t_min, dh, di, dt, dp, dn, dff);
+    } else if (use_tensor_scan(c, d)) {
+        using Shape = UmmaShape<RT_UMMA_GROUPS, RT_UMMA_CHUNK>;
+        auto k = hitlist_kernel_umma<RT_UMMA_GROUPS, RT_UMMA_CHUNK>;
+        const size_t sm = Shape::smem_bytes(d.scene.u_npad);
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        k<<<(unsigned)((n + Shape::kRayThreads - 1) / Shape::kRayThreads), Shape::kThreads, sm, d.stream>>>(scene, n, dor, dd, t_min, dh, di, dt, dp, dn, dff);
     } else {
         const ScanCfg cfg = pick_cfg(d.scene.np);
         if (cfg.variant == 0) {
-            hitlist_kernel<float, true, 256><<<grid, 256, cfg.smem, d.stream>>>(scene, n, dor, dd, t_min, dh, di, dt, dp, dn, dff);
+            auto k = hitlist_kernel<float, true, 256>;
+            if (cfg.smem > 48 * 1024) CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+            k<<<grid, 256, cfg.smem, d.stream>>>(scene, n, dor, dd, t_min, dh, di, dt, dp, dn, dff);
         } else if (cfg.variant == 1) {
             auto k = hitlist_kernel<float, true, 512>;
             CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
@@ -735,6 +830,8 @@ extern "C" int rtiow_scatter_batch(rtiow_ctx* c, int precision, int64_t n, const
                                    const double* sample, int32_t* some, double* attenuation, double* s_orig, double* s_dir)
 {
     BATCH_PROLOGUE();
+    if (!kind || !albedo || !param || !r_orig || !r_dir || !p || !normal || !front_face || !sample || !some || !attenuation || !s_orig || !s_dir)
+        return fail(RTIOW_ERR_INVALID_ARG, "NULL array");
     if (n == 0) return RTIOW_OK;
     for (int64_t i = 0; i < n; ++i) if (kind[i] < 0 || kind[i] > RTIOW_MAT_DIELECTRIC) return fail(RTIOW_ERR_UNSUPPORTED, "item %lld: material kind %d", (long long)i, kind[i]);
     int32_t *dk, *dff, *dsome; double *da, *dpar, *dro, *drd, *dp, *dn, *dsm, *datt, *dso, *dsd;
@@ -753,7 +850,7 @@ extern "C" int rtiow_get_ray_batch(rtiow_ctx* c, int precision, const rtiow_came
                                    const double* disk_xy, double* orig, double* dir)
 {
     BATCH_PROLOGUE();
-    if (!cam) return fail(RTIOW_ERR_INVALID_ARG, "cam is NULL");
+    if (!cam || !s || !t || !disk_xy || !orig || !dir) return fail(RTIOW_ERR_INVALID_ARG, "NULL argument");
     if (n == 0) return RTIOW_OK;
     double *ds, *dt, *dk, *dor, *dd;
     CU(S.in(s, n, &ds)); CU(S.in(t, n, &dt)); CU(S.in(disk_xy, (size_t)n * 2, &dk)); CU(S.out(N3, &dor)); CU(S.out(N3, &dd));
@@ -769,6 +866,7 @@ extern "C" int rtiow_to_rgba_batch(rtiow_ctx* c, int precision, int64_t n, const
 {
     BATCH_PROLOGUE();
     if (spp == 0) return fail(RTIOW_ERR_INVALID_ARG, "spp must be >= 1");
+    if (!color || !out_rgba) return fail(RTIOW_ERR_INVALID_ARG, "NULL array");
     if (n == 0) return RTIOW_OK;
     double* dc; uint32_t* dout;
     CU(S.in(color, N3, &dc)); CU(S.out(n, &dout));
@@ -783,6 +881,7 @@ extern "C" int rtiow_to_rgba_batch(rtiow_ctx* c, int precision, int64_t n, const
 extern "C" int rtiow_reflect_batch(rtiow_ctx* c, int precision, int64_t n, const double* v, const double* nrm, double* out)
 {
     BATCH_PROLOGUE();
+    if (!v || !nrm || !out) return fail(RTIOW_ERR_INVALID_ARG, "NULL array");
     if (n == 0) return RTIOW_OK;
     double *dv, *dn, *dout;
     CU(S.in(v, N3, &dv)); CU(S.in(nrm, N3, &dn)); CU(S.out(N3, &dout));
@@ -797,6 +896,7 @@ extern "C" int rtiow_reflect_batch(rtiow_ctx* c, int precision, int64_t n, const
 extern "C" int rtiow_refract_batch(rtiow_ctx* c, int precision, int64_t n, const double* uv, const double* nrm, const double* eta, double* out)
 {
     BATCH_PROLOGUE();
+    if (!uv || !nrm || !eta || !out) return fail(RTIOW_ERR_INVALID_ARG, "NULL array");
     if (n == 0) return RTIOW_OK;
     double *dv, *dn, *de, *dout;
     CU(S.in(uv, N3, &dv)); CU(S.in(nrm, N3, &dn)); CU(S.in(eta, n, &de)); CU(S.out(N3, &dout));
@@ -811,30 +911,53 @@ extern "C" int rtiow_refract_batch(rtiow_ctx* c, int precision, int64_t n, const
 extern "C" int rtiow_ray_color_batch(rtiow_ctx* c, int precision, int64_t n, const double* orig, const double* dir, const uint32_t* pixel,
                                      const uint32_t* sample, uint64_t seed, int32_t max_depth, double t_min, double* color, uint64_t* rays)
 {
+    return rtiow_ray_color_trace_batch(c, precision, n, orig, dir, pixel, sample, seed, max_depth, t_min, color, rays, nullptr, nullptr);
+}
+
+extern "C" int rtiow_ray_color_trace_batch(rtiow_ctx* c, int precision, int64_t n, const double* orig, const double* dir, const uint32_t* pixel,
+                                           const uint32_t* sample, uint64_t seed, int32_t max_depth, double t_min, double* color, uint64_t* rays,
+                                           int32_t* trace_index, double* trace_ray)
+{
     BATCH_PROLOGUE();
     if (!d.has_scene) return fail(RTIOW_ERR_INVALID_ARG, "no scene uploaded");
+    if (!orig || !dir || !pixel || !sample || !color) return fail(RTIOW_ERR_INVALID_ARG, "NULL array");
+    if (precision == RTIOW_PRECISION_F32) { int rc = check_scan_backend(c, d); if (rc) return rc; }
     if (n == 0) return RTIOW_OK;
     SceneDev scene = d.scene;
     double *dor, *dd, *dcol; uint32_t *dpx, *dsm; unsigned long long* dr;
     CU(S.in(orig, N3, &dor)); CU(S.in(dir, N3, &dd)); CU(S.in(pixel, n, &dpx)); CU(S.in(sample, n, &dsm));
     CU(S.out(N3, &dcol)); CU(S.out(n, &dr));
+    const size_t n_tr = (size_t)n * (size_t)std::max(max_depth, 0);
+    int32_t* dti = nullptr; double* dtr = nullptr;
+    if (trace_index && n_tr) { CU(S.out(n_tr, &dti)); CU(cudaMemsetAsync(dti, 0xff, n_tr * sizeof(int32_t), d.stream)); }   // -1: no ray at this depth
+    if (trace_ray && n_tr) CU(S.out(n_tr * 6, &dtr));
     if (precision == RTIOW_PRECISION_F64) {
-        ray_color_kernel<double, false, 256><<<grid, 256, 0, d.stream>>>(scene, n, dor, dd, dpx, dsm, seed, max_depth, t_min, dcol, dr);
+        ray_color_kernel<double, false, 256><<<grid, 256, 0, d.stream>>>(scene, n, dor, dd, dpx, dsm, seed, max_depth, t_min, dcol, dr, dti, dtr);
+    } else if (use_tensor_scan(c, d)) {
+        using Shape = UmmaShape<RT_UMMA_GROUPS, RT_UMMA_CHUNK>;
+        auto k = ray_color_kernel_umma<RT_UMMA_GROUPS, RT_UMMA_CHUNK>;
+        const size_t sm = Shape::smem_bytes(d.scene.u_npad);
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        k<<<(unsigned)((n + Shape::kRayThreads - 1) / Shape::kRayThreads), Shape::kThreads, sm, d.stream>>>(scene, n, dor, dd, dpx, dsm, seed, max_depth, t_min, dcol, dr, dti, dtr);
     } else {
         const ScanCfg cfg = pick_cfg(d.scene.np);
         if (cfg.variant == 0) {
-            ray_color_kernel<float, true, 256><<<grid, 256, cfg.smem, d.stream>>>(scene, n, dor, dd, dpx, dsm, seed, max_depth, t_min, dcol, dr);
+            auto k = ray_color_kernel<float, true, 256>;
+            if (cfg.smem > 48 * 1024) CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+            k<<<grid, 256, cfg.smem, d.stream>>>(scene, n, dor, dd, dpx, dsm, seed, max_depth, t_min, dcol, dr, dti, dtr);
         } else if (cfg.variant == 1) {
             auto k = ray_color_kernel<float, true, 512>;
             CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
-            k<<<(unsigned)((n + 511) / 512), 512, cfg.smem, d.stream>>>(scene, n, dor, dd, dpx, dsm, seed, max_depth, t_min, dcol, dr);
+            k<<<(unsigned)((n + 511) / 512), 512, cfg.smem, d.stream>>>(scene, n, dor, dd, dpx, dsm, seed, max_depth, t_min, dcol, dr, dti, dtr);
         } else {
-            ray_color_kernel<float, false, 256><<<grid, 256, cfg.smem, d.stream>>>(scene, n, dor, dd, dpx, dsm, seed, max_depth, t_min, dcol, dr);
+            ray_color_kernel<float, false, 256><<<grid, 256, cfg.smem, d.stream>>>(scene, n, dor, dd, dpx, dsm, seed, max_depth, t_min, dcol, dr, dti, dtr);
         }
     }
     CU(cudaGetLastError());
     CU(S.back(color, dcol, N3));
     if (rays) CU(S.back((unsigned long long*)rays, dr, n));
+    if (dti) CU(S.back(trace_index, dti, n_tr));
+    if (dtr) CU(S.back(trace_ray, dtr, n_tr * 6));
     CU(cudaStreamSynchronize(d.stream));
     return RTIOW_OK;
 }
@@ -843,6 +966,7 @@ extern "C" int rtiow_sampler_batch(rtiow_ctx* c, int precision, int64_t n, const
                                    uint64_t seed, double* out)
 {
     BATCH_PROLOGUE();
+    if (!pixel || !sample || !bounce || !out) return fail(RTIOW_ERR_INVALID_ARG, "NULL array");
     if (n == 0) return RTIOW_OK;
     uint32_t *dp, *ds, *db; double* dout;
     CU(S.in(pixel, n, &dp)); CU(S.in(sample, n, &ds)); CU(S.in(bounce, n, &db)); CU(S.out((size_t)n * 12, &dout));

@@ -9,6 +9,7 @@
 // so the image is bit-identical for any chunk size, grid size or GPU count.
 #pragma once
 #include "rt_scene.cuh"
+#include "rt_umma_scan.cuh"
 
 namespace rt {
 
@@ -153,10 +154,11 @@ __device__ __forceinline__ void event_sample(bool camera, const Uniform4<T>& u, 
 // different order (scatter of the previous hit and camera rays share one Philox block + sampler per iteration).
 template <typename T, bool kSmem>
 __device__ __forceinline__ bool bounce_step(const SceneDev& sc, const float* table, uint16_t* cand, int cand_stride, const PhiloxKey& key, int max_depth,
-                                            T t_min, bool active, PathState<T>& ps, V3<T>* radiance)
+                                            T t_min, bool active, PathState<T>& ps, V3<T>* radiance, int* hit_index = nullptr)
 {
     T t_hit; int idx, code;
     world_hit<T, kSmem>(sc, table, cand, cand_stride, ps, &t_hit, &idx, &code);
+    if (hit_index) *hit_index = idx;
     if (!active) return false;
     if (idx < 0) {                                                            // miss: sky (main.rs:54-56)
         *radiance = ps.thr * sky<T, sizeof(T) == 4>(ps.dhat);
@@ -294,6 +296,61 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) render_kernel(const Render
         }
     }
     if (lane == 0) atomicAdd(a.ray_counter, (unsigned long long)n_rays_w);
+}
+
+// The same render loop with the sphere filter on the tensor cores (rt_umma_scan.cuh): G groups of 128 ray threads + G
+// MMA-issuer warps per CTA, one CTA per SM.  Everything per ray — work distribution, the Philox event, camera / scatter,
+// the precise test of the filter's survivors, the f64 large-sphere test, accumulation — is the code above; only the
+// filter moves from 7 FFMA2 per sphere pair to three tcgen05.mma per 128 rays x NC spheres, and the warp-level "any lane
+// alive" vote becomes a 128-thread one, because a group's 128 rays form one MMA.
+template <int G, int NC>
+__global__ void __launch_bounds__(G * 160, 1) render_kernel_umma(const RenderArgs<float> a)
+{
+    extern __shared__ __align__(1024) unsigned char smem_umma[];
+    uint32_t tmem_base;
+    UmmaCtx ux = umma_setup<G, NC>(smem_umma, a.scene, &tmem_base);
+    const unsigned lane = threadIdx.x & 31u;
+    if (ux.issuer_warp) {
+        if (lane == 0) umma_issuer<NC>(ux);
+    } else {
+        const unsigned lt_mask = (1u << lane) - 1u;
+        PathState<float> ps; init_path(ps);
+        uint32_t acc_lp = 0;
+        bool pending = false;
+        int hit_idx = -1, hit_code = RT_SELF_NONE;
+        uint32_t n_rays_w = 0;
+        WorkCursor wc;
+        for (;;) {
+            uint32_t px = 0, pj = 0;
+            const bool fresh = assign_work(a, wc, lt_mask, pending, ps, acc_lp, &px, &pj);
+            if (!umma_group_any(ux, fresh || pending)) { umma_group_quit(ux); break; }
+
+            const Uniform4<float> u = event_uniforms<float>(a.key, ps.pix_key, ps.smp, fresh ? 0u : (uint32_t)(a.max_depth - ps.depth) + 1u);
+            float sa, sb, z; event_sample(fresh, u, &sa, &sb, &z);
+            bool active = false;
+            if (fresh) {
+                const float su = (float(px) + u.u0) * a.inv_wm1;             // main.rs:131
+                const float sv = (float(pj) + u.u1) * a.inv_hm1;             // main.rs:132
+                V3<float> ro, rd; get_ray(a.cam, su, sv, sa, sb, &ro, &rd);  // main.rs:134
+                start_ray(ps, ro, rd, a.t_min);
+                ps.thr = mk<float>(1, 1, 1); ps.self_code = RT_SELF_NONE;
+                ps.depth = a.max_depth;
+                active = ps.depth > 0;                                       // main.rs:40-42
+            } else if (pending) {
+                active = scatter_at_hit(a.scene, a.t_min, ps, ps.o, hit_idx, hit_code, sa, sb, z, u.u0, u.u2);
+            }
+            pending = false;
+
+            n_rays_w += __popc(__ballot_sync(RT_FULL, active));              // world.hit call count (main.rs:44)
+            const HitF h = closest_hit_umma<G, NC>(ux, a.scene, ps.o, ps.dhat, ps.tmin_n, ps.self_code, ps.self_n);
+            if (active) {
+                if (h.idx < 0) accumulate(a, acc_lp, ps.thr * sky<float, true>(ps.dhat));                    // miss: sky (main.rs:54-56)
+                else { ps.o = ps.o + ps.dhat * h.t; hit_idx = h.idx; hit_code = h.code; pending = true; }    // ray.rs:15-17
+            }
+        }
+        if (lane == 0) atomicAdd(a.ray_counter, (unsigned long long)n_rays_w);
+    }
+    umma_teardown(tmem_base);
 }
 
 // Color::to_rgba (vec3.rs:404-420) + the row flip (main.rs:141-145): fixed-point sums -> top-down

@@ -16,6 +16,7 @@
 //   mat      float4 / double4 [n]  (albedo r,g,b, fuzz|ir) resolved per sphere; kind uint8 [n]
 #pragma once
 #include "rt_device.cuh"
+#include "rt_umma.cuh"
 
 namespace rt {
 
@@ -36,6 +37,12 @@ struct SceneDev {
     const double4* matd;
     const uint8_t* kind;
     int n;
+    // tensor-core filter (rt_umma.cuh, rt_umma_scan.cuh): the small spheres' feature rows, fp16 hi/lo, in the canonical
+    // K-major layout tcgen05.mma reads from shared memory; u_npad = 0 when the scene does not qualify (too large for
+    // shared memory, or so spread out that the fp16 split's slack would swamp the spheres)
+    const unsigned char* u_bimg;   // [2][u_npad * 32] bytes: hi block, lo block
+    int u_npad;                    // small spheres padded to a whole number of MMA chunks (never-pass entries)
+    umma::FeatScale u_sc;
 };
 
 #define RT_FULL 0xffffffffu

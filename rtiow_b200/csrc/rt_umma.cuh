@@ -141,7 +141,8 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) { __half2 h = __fl
 
 // The ray's A rows: hi[8] / lo[8] hold 16 fp16 each (features 0..10, then zeros).  (o, dhat): any point of the line and
 // its (nearly) unit direction; `live` false -> the line cannot touch any sphere of the table and every product is < 0.
-__device__ __forceinline__ void ray_features(float ox, float oy, float oz, float dx, float dy, float dz, bool live, const FeatScale sc,
+// `sigma` >= 0 is a per-ray slack added to the discriminant (it multiplies S_10 = 1).
+__device__ __forceinline__ void ray_features(float ox, float oy, float oz, float dx, float dy, float dz, bool live, float sigma, const FeatScale sc,
                                              uint32_t (&hi)[8], uint32_t (&lo)[8])
 {
     const float a = dx * dx + dy * dy + dz * dz;
@@ -153,7 +154,7 @@ __device__ __forceinline__ void ray_features(float ox, float oy, float oz, float
     R[4] = dx * dx * sc.s4; R[5] = dy * dy * sc.s4; R[6] = dz * dz * sc.s4;
     const float two_s4 = 2.0f * sc.s4;
     R[7] = dx * dy * two_s4; R[8] = dx * dz * two_s4; R[9] = dy * dz * two_s4;
-    R[10] = (fd * fd - a * (ox * ox + oy * oy + oz * oz)) * sc.s10;
+    R[10] = (fd * fd - a * (ox * ox + oy * oy + oz * oz) + sigma) * sc.s10;
     R[11] = 0.0f;
     if (!live) {
 #pragma unroll

@@ -1,0 +1,208 @@
+// rt_umma_scan.cuh — HittableList::hit (/root/reference/src/shapes/mod.rs:56-69) with the sphere filter on the tensor cores.
+//
+// CTA = G ray groups of 128 threads (4 warps: warp q of a group owns TMEM lanes [32q, 32q+32)) + G issuer warps.
+// One scan of a group = 128 rays against every small sphere of the scene:
+//   ray threads   : feature rows of the ray (rt_umma.cuh) -> tcgen05.st into the group's A columns -> arrive(a_full)
+//   issuer thread : wait(a_full); per chunk of NC spheres: wait(empty) ; 3 x tcgen05.mma (hi.hi + hi.lo + lo.hi) into the
+//                   group's D columns ; tcgen05.commit -> full
+//   ray threads   : wait(full) ; tcgen05.ld their own lane: NC discriminants of THEIR ray ; arrive(empty) ; funnel-shift
+//                   the sign bits into 32-sphere words ; survivors -> per-lane candidate list -> precise test
+//                   (sphere_roots, rt_device.cuh), exactly as the FP32 scan of rt_scene.cuh does.
+// The issuer is a warp of its own because tcgen05.mma issue stalls the issuing thread while the tensor pipe is busy
+// (tools/probe_umma_filter.cu: an issuer that shares a warp with an epilogue halves the throughput).  D is single-buffered
+// per group: while one group's MMAs run, the other groups collect signs, so the tensor pipe and the ALU pipe overlap
+// across groups (G = 4, NC = 64: 143.6 TFLOP/s-equivalent stand-alone against 65.8 for the FP32 filter).
+// Each CTA owns all 512 TMEM columns, so exactly one CTA may live on an SM: the launch asks for more than half of the
+// SM's shared memory.
+#pragma once
+#include "rt_scene.cuh"
+#include "rt_umma.cuh"
+
+namespace rt {
+
+#define RT_UMMA_GROUPS 4                      // ray groups per CTA in the product kernels (16 ray warps + 4 issuer warps = 640 threads)
+#define RT_UMMA_CHUNK 64                      // spheres per MMA chunk (TMEM: 4 x (64 + 16) = 320 of 512 columns)
+#define RT_UMMA_MIN_SMEM (120 * 1024)        // > half an SM's shared memory: one CTA per SM (each CTA allocates all of TMEM)
+
+template <int G, int NC> struct UmmaShape {
+    static_assert(NC % 32 == 0 && NC >= 32 && NC <= 256, "chunk = whole 32-sphere words");
+    static constexpr int kRayThreads = G * 128, kThreads = G * 160;
+    static constexpr int kCols = NC + 16;                        // TMEM columns per group: D (NC) + A_hi (8) + A_lo (8)
+    static_assert(G * kCols <= 512, "TMEM has 512 columns");
+    static constexpr size_t kCandBytes = (size_t)kRayThreads * RT_CAND_CAP * sizeof(uint16_t);
+    __host__ __device__ static constexpr size_t b_offset_bytes() { return (kCandBytes + 127) & ~(size_t)127; }
+    __host__ __device__ static size_t bars_offset_bytes(int npad) { return b_offset_bytes() + 2 * RT_UMMA_B_BLOCK_BYTES(npad); }
+    __host__ __device__ static size_t smem_bytes(int npad)
+    {
+        const size_t need = bars_offset_bytes(npad) + (size_t)G * 8 * 8 + 16 + (size_t)G * 4;
+        return need > RT_UMMA_MIN_SMEM ? need : (size_t)RT_UMMA_MIN_SMEM;
+    }
+};
+
+// per-thread view of its group's resources
+struct UmmaCtx {
+    uint32_t t_d, t_a;              // TMEM columns of the group's D and A (A_hi at t_a, A_lo at t_a + 8); lane field 0
+    uint32_t lane_base;             // this warp's TMEM lane quarter, in the address's lane field
+    uint32_t bar_afull, bar_full, bar_empty;
+    uint32_t s_hi, s_lo;            // shared-window addresses of the B image's two K blocks
+    uint32_t full_phase;            // parity of the next phase of `full` to wait for
+    int n_chunks;
+    int group, tid_in_group;
+    bool issuer_warp;
+    volatile int* quit;             // the group's "no more scans" flag, read by its issuer after a_full
+    uint16_t* cand;                 // this lane's first candidate slot (slot k at cand[k * kRayThreads])
+};
+
+// All threads of the CTA.  Stages the B image, initialises the groups' mbarriers, allocates TMEM.
+template <int G, int NC>
+__device__ __forceinline__ UmmaCtx umma_setup(unsigned char* smem_raw, const SceneDev& sc, uint32_t* tmem_base_out)
+{
+    using S = UmmaShape<G, NC>;
+    using namespace umma;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    unsigned char* b_img = smem_raw + S::b_offset_bytes();
+    const size_t blk = RT_UMMA_B_BLOCK_BYTES(sc.u_npad);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + S::bars_offset_bytes(sc.u_npad));       // [G][8]: a_full, full, empty
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + G * 8);
+    int* quit = reinterpret_cast<int*>(tmem_slot + 4);
+    for (size_t i = (size_t)tid * 16; i < 2 * blk; i += (size_t)S::kThreads * 16)
+        *reinterpret_cast<uint4*>(b_img + i) = *reinterpret_cast<const uint4*>(sc.u_bimg + i);
+    if (tid == 0) {
+        for (int i = 0; i < G; ++i) {
+            mbar_init(smem_u32(bars + 8 * i + 0), 128);       // every ray thread of the group
+            mbar_init(smem_u32(bars + 8 * i + 1), 1);         // tcgen05.commit
+            mbar_init(smem_u32(bars + 8 * i + 2), 4);         // lane 0 of the group's four warps
+            quit[i] = 0;
+        }
+        fence_mbar_init();
+    }
+    __syncwarp();
+    if (warp == 0) { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
+    fence_proxy_async_smem();                    // B was written with generic stores; the tensor core reads it through the async proxy
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    *tmem_base_out = tmem_base;
+
+    UmmaCtx ux;
+    ux.issuer_warp = warp >= 4 * G;
+    ux.group = ux.issuer_warp ? warp - 4 * G : warp >> 2;
+    ux.tid_in_group = ux.issuer_warp ? lane : (tid & 127);
+    ux.t_d = tmem_base + (uint32_t)(ux.group * S::kCols);
+    ux.t_a = ux.t_d + NC;
+    ux.lane_base = (uint32_t)(32 * (warp & 3)) << 16;
+    ux.bar_afull = smem_u32(bars + 8 * ux.group); ux.bar_full = ux.bar_afull + 8; ux.bar_empty = ux.bar_afull + 16;
+    ux.s_hi = smem_u32(b_img); ux.s_lo = ux.s_hi + (uint32_t)blk;
+    ux.full_phase = 0;
+    ux.n_chunks = sc.u_npad / NC;
+    ux.quit = quit + ux.group;
+    ux.cand = reinterpret_cast<uint16_t*>(smem_raw) + (ux.issuer_warp ? 0 : tid);
+    return ux;
+}
+
+// The group's MMA issuer: ONE thread.  Returns when the group's ray threads have called umma_group_quit.
+template <int NC>
+__device__ __forceinline__ void umma_issuer(const UmmaCtx& ux)
+{
+    using namespace umma;
+    const uint32_t idesc = make_idesc_f16_f32(NC);
+    uint32_t a_phase = 0, e_phase = 0; bool used = false;
+    for (;;) {
+        mbar_wait(ux.bar_afull, a_phase); a_phase ^= 1u;                  // all 128 feature rows are in TMEM — or the group is done
+        if (*ux.quit) break;
+        tc_fence_after();
+        for (int c = 0; c < ux.n_chunks; ++c) {
+            if (used) { mbar_wait(ux.bar_empty, e_phase); e_phase ^= 1u; tc_fence_after(); }     // the previous chunk's D has been read
+            used = true;
+            const uint32_t off = (uint32_t)(c * (NC / 8)) * RT_UMMA_B_SBO;
+            const uint64_t dh = make_smem_desc(ux.s_hi + off, RT_UMMA_B_LBO, RT_UMMA_B_SBO), dl = make_smem_desc(ux.s_lo + off, RT_UMMA_B_LBO, RT_UMMA_B_SBO);
+            mma_f16_ts(ux.t_d, ux.t_a, dh, idesc, 0u);                    // hi . hi
+            mma_f16_ts(ux.t_d, ux.t_a, dl, idesc, 1u);                    // hi . lo
+            mma_f16_ts(ux.t_d, ux.t_a + 8u, dh, idesc, 1u);               // lo . hi
+            tc_commit(ux.bar_full);
+        }
+    }
+}
+
+// group-wide OR of a predicate over the 128 ray threads (one named barrier per group)
+__device__ __forceinline__ bool umma_group_any(const UmmaCtx& ux, bool pred) { return umma::named_bar_or(1 + ux.group, 128, pred); }
+// every ray thread of the group, once, after its last scan: releases the group's issuer
+__device__ __forceinline__ void umma_group_quit(const UmmaCtx& ux)
+{
+    if (ux.tid_in_group == 0) *ux.quit = 1;
+    umma::mbar_arrive(ux.bar_afull);             // release; the issuer's wait acquires and then reads the flag
+}
+// all threads of the CTA, last thing
+__device__ __forceinline__ void umma_teardown(uint32_t tmem_base)
+{
+    umma::tc_fence_before();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0) umma::tmem_dealloc(tmem_base, 512);
+}
+
+// Closest hit of one ray against the whole scene — the tensor-core twin of closest_hit<kSmem> (rt_scene.cuh); every one of
+// the group's 128 ray threads must call together (lanes without a ray pass anything: their result is ignored).
+template <int G, int NC>
+__device__ __forceinline__ HitF closest_hit_umma(UmmaCtx& ux, const SceneDev& sc, V3<float> o, V3<float> dhat, float t_min, int self_code, V3<float> self_n)
+{
+    using namespace umma;
+    constexpr int kStride = UmmaShape<G, NC>::kRayThreads;
+    const float inv_a = 2.0f - length_squared(dhat);           // 1/a for a = 1 + e, |e| < 1e-6
+    float tb = __int_as_float(0x7f800000);                     // f64::INFINITY at main.rs:44
+    int pb = -1;
+    // the sphere the ray starts on is tested on its own, independently of the filter (rt_scene.cuh, candidate_self)
+    if (self_code >= 0) candidate_self<float>(dhat, inv_a, t_min, self_n, sc.small[self_code].w, self_code, &tb, &pb);
+
+    // the line's foot point of the coordinate origin, orthogonalised twice (a far origin leaves O(u |o|) along dhat after one pass)
+    V3<float> f = o - dhat * (dot(o, dhat) * inv_a);
+    f = f - dhat * (dot(f, dhat) * inv_a);
+    const float sigma = sc.filter_sigma * (fabsf(o.x) + fabsf(o.y) + fabsf(o.z));     // covers the f32 error of a far origin's foot point
+    const bool live = length_squared(f) < sc.filter_R2 + sigma;                        // a line that misses the bounding sphere hits nothing
+    uint32_t hi[8], lo[8];
+    ray_features(f.x, f.y, f.z, dhat.x, dhat.y, dhat.z, live, sigma, sc.u_sc, hi, lo);
+    tmem_st8(ux.t_a + ux.lane_base, hi);
+    tmem_st8(ux.t_a + 8u + ux.lane_base, lo);
+    tc_wait_st();
+    tc_fence_before();
+    mbar_arrive(ux.bar_afull);
+
+    int nc = 0;
+    for (int c = 0; c < ux.n_chunks; ++c) {
+        mbar_wait(ux.bar_full, ux.full_phase); ux.full_phase ^= 1u;
+        tc_fence_after();
+        uint32_t v[NC / 32][32];
+#pragma unroll
+        for (int w = 0; w < NC / 32; ++w) tmem_ld32(ux.t_d + ux.lane_base + 32u * w, v[w]);
+        tc_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(ux.bar_empty);            // the issuer may overwrite D: the next chunk's MMAs overlap the sign collection
+#pragma unroll
+        for (int w = 0; w < NC / 32; ++w) {
+            unsigned m = 0;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) m = __funnelshift_l(v[w][k], m, 1);          // bit (31-k) = sign of sphere k's discriminant
+            unsigned pass = ~m;                                                       // set: the sphere passed the filter
+            while (pass) {
+                const int k = __clz(pass);
+                pass &= ~(0x80000000u >> k);
+                const int p = c * NC + w * 32 + k;
+                if (nc < RT_CAND_CAP) { ux.cand[nc * kStride] = (uint16_t)p; ++nc; }
+                else if (p != self_code) { const float4 s = sc.small[p]; candidate<float, true>(o, dhat, inv_a, t_min, mk(s.x, s.y, s.z), s.w, p, &tb, &pb); }
+            }
+        }
+    }
+    const int nmax = __reduce_max_sync(RT_FULL, nc);
+    for (int k = 0; k < nmax; ++k) {
+        if (k < nc) {
+            const int p = ux.cand[k * kStride];
+            if (p != self_code) { const float4 s = sc.small[p]; candidate<float, true>(o, dhat, inv_a, t_min, mk(s.x, s.y, s.z), s.w, p, &tb, &pb); }
+        }
+    }
+    HitF h; h.t = tb; h.idx = pb >= 0 ? sc.small_idx[pb] : -1; h.code = pb;
+    if (sc.nb > 0) h = big_spheres_hit(sc.big, sc.big_idx, sc.nb, o, dhat, t_min, self_code, self_n, h);
+    return h;
+}
+
+}  // namespace rt

@@ -67,6 +67,35 @@ __global__ void __launch_bounds__(kThreads) hitlist_kernel(SceneDev sc, int64_t 
     st3(p, i, pp); st3(normal, i, nn); front_face[i] = ff ? 1 : 0;
 }
 
+// the same through the tensor-core scan (rt_umma_scan.cuh): 128 rays per group, G groups + G issuer warps per CTA
+template <int G, int NC>
+__global__ void __launch_bounds__(G * 160, 1) hitlist_kernel_umma(SceneDev sc, int64_t n, const double* orig, const double* dir, double t_min,
+                                                                  int32_t* hit, int32_t* index, double* t, double* p, double* normal, int32_t* front_face)
+{
+    extern __shared__ __align__(1024) unsigned char smem_umma[];
+    uint32_t tmem_base;
+    UmmaCtx ux = umma_setup<G, NC>(smem_umma, sc, &tmem_base);
+    if (ux.issuer_warp) {
+        if ((threadIdx.x & 31) == 0) umma_issuer<NC>(ux);
+    } else {
+        const int64_t i = (int64_t)blockIdx.x * (G * 128) + threadIdx.x;
+        const bool live = i < n;
+        V3<float> o = mk<float>(0, 0, 0), d = mk<float>(0, 1, 0);
+        if (live) { o = ld3<float>(orig, i); d = ld3<float>(dir, i); }
+        const float len = length(d), inv_len = 1.0f / len;
+        const V3<float> dhat = d * inv_len;
+        const HitF h = closest_hit_umma<G, NC>(ux, sc, o, dhat, (float)t_min * len, RT_SELF_NONE, mk<float>(0, 1, 0));
+        umma_group_quit(ux);
+        if (live) {
+            V3<float> pp = mk<float>(0, 0, 0), nn = mk<float>(0, 0, 0); bool ff = false;
+            if (h.idx >= 0) { const float4 s = sc.sph[h.idx]; pp = o + dhat * h.t; hit_record(pp, mk<float>(s.x, s.y, s.z), s.w, dhat, &nn, &ff); }
+            hit[i] = h.idx >= 0; index[i] = h.idx; t[i] = h.idx >= 0 ? (double)(h.t * inv_len) : 0.0;
+            st3(p, i, pp); st3(normal, i, nn); front_face[i] = ff ? 1 : 0;
+        }
+    }
+    umma_teardown(tmem_base);
+}
+
 // Scatter::scatter (materials.rs:22-30,50-61,77-104)
 template <typename T>
 __global__ void scatter_kernel(int64_t n, const int32_t* kind, const double* albedo, const double* param, const double* r_orig,
@@ -134,7 +163,7 @@ __global__ void sampler_kernel(int64_t n, const uint32_t* pixel, const uint32_t*
 template <typename T, bool kSmem, int kThreads>
 __global__ void __launch_bounds__(kThreads) ray_color_kernel(SceneDev sc, int64_t n, const double* orig, const double* dir, const uint32_t* pixel,
                                                              const uint32_t* sample, uint64_t seed, int32_t max_depth, double t_min,
-                                                             double* color, unsigned long long* rays)
+                                                             double* color, unsigned long long* rays, int32_t* trace_idx, double* trace_ray)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint16_t* cand;
@@ -150,11 +179,56 @@ __global__ void __launch_bounds__(kThreads) ray_color_kernel(SceneDev sc, int64_
     while (__any_sync(RT_FULL, active)) {
         V3<T> rad = mk<T>(0, 0, 0);
         const bool was = active;
-        if (active) ++nr;                                                     // world.hit call count (main.rs:44)
-        active = bounce_step<T, kSmem>(sc, table, cand, kThreads, key, max_depth, (T)t_min, active, ps, &rad);
+        if (active) {
+            if (trace_ray) { double* tr = trace_ray + ((size_t)i * max_depth + nr) * 6; tr[0] = ps.o.x; tr[1] = ps.o.y; tr[2] = ps.o.z; tr[3] = ps.dhat.x; tr[4] = ps.dhat.y; tr[5] = ps.dhat.z; }
+            ++nr;                                                             // world.hit call count (main.rs:44)
+        }
+        int hit_index = -1;
+        active = bounce_step<T, kSmem>(sc, table, cand, kThreads, key, max_depth, (T)t_min, active, ps, &rad, &hit_index);
+        if (was && trace_idx) trace_idx[(size_t)i * max_depth + nr - 1] = hit_index;
         if (was && !active) result = rad;
     }
     if (i < n) { st3(color, i, result); if (rays) rays[i] = nr; }
+}
+
+// ray_color through the tensor-core scan: the bounce loop of bounce_step, 128 rays per group in lock step
+template <int G, int NC>
+__global__ void __launch_bounds__(G * 160, 1) ray_color_kernel_umma(SceneDev sc, int64_t n, const double* orig, const double* dir, const uint32_t* pixel,
+                                                                    const uint32_t* sample, uint64_t seed, int32_t max_depth, double t_min,
+                                                                    double* color, unsigned long long* rays, int32_t* trace_idx, double* trace_ray)
+{
+    extern __shared__ __align__(1024) unsigned char smem_umma[];
+    uint32_t tmem_base;
+    UmmaCtx ux = umma_setup<G, NC>(smem_umma, sc, &tmem_base);
+    if (ux.issuer_warp) {
+        if ((threadIdx.x & 31) == 0) umma_issuer<NC>(ux);
+    } else {
+        const int64_t i = (int64_t)blockIdx.x * (G * 128) + threadIdx.x;
+        bool active = i < n && max_depth > 0;
+        PathState<float> ps; init_path(ps);
+        ps.thr = mk<float>(1, 1, 1); ps.depth = max_depth;
+        const PhiloxKey key = philox_key(seed);
+        V3<float> result = mk<float>(0, 0, 0);
+        uint32_t nr = 0;
+        if (i < n) { start_ray(ps, ld3<float>(orig, i), ld3<float>(dir, i), (float)t_min); ps.pix_key = pixel[i]; ps.smp = sample[i]; }
+        while (umma_group_any(ux, active)) {
+            if (active) {
+                if (trace_ray) { double* tr = trace_ray + ((size_t)i * max_depth + nr) * 6; tr[0] = ps.o.x; tr[1] = ps.o.y; tr[2] = ps.o.z; tr[3] = ps.dhat.x; tr[4] = ps.dhat.y; tr[5] = ps.dhat.z; }
+                ++nr;                                                             // world.hit call count (main.rs:44)
+            }
+            const HitF h = closest_hit_umma<G, NC>(ux, sc, ps.o, ps.dhat, ps.tmin_n, ps.self_code, ps.self_n);
+            if (!active) continue;
+            if (trace_idx) trace_idx[(size_t)i * max_depth + nr - 1] = h.idx;
+            if (h.idx < 0) { result = ps.thr * sky<float, true>(ps.dhat); active = false; continue; }         // main.rs:54-56
+            const V3<float> p = ps.o + ps.dhat * h.t;                             // ray.rs:15-17
+            const Uniform4<float> u = event_uniforms<float>(key, ps.pix_key, ps.smp, (uint32_t)(max_depth - ps.depth) + 1u);
+            float sa, sb, z; event_sample(false, u, &sa, &sb, &z);
+            if (!scatter_at_hit(sc, (float)t_min, ps, p, h.idx, h.code, sa, sb, z, u.u0, u.u2)) { result = mk<float>(0, 0, 0); active = false; }
+        }
+        umma_group_quit(ux);
+        if (i < n) { st3(color, i, result); if (rays) rays[i] = nr; }
+    }
+    umma_teardown(tmem_base);
 }
 
 // ---- FP32-pipe calibration kernels (roofline denominator) -----------------------------------------

@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(G * 160, 1) probe_kernel(const ProbeArgs a)
             fx -= t * dx; fy -= t * dy; fz -= t * dz;
             const bool live = fx * fx + fy * fy + fz * fz < a.R2;
             uint32_t hi[8], lo[8];
-            ray_features(fx, fy, fz, dx, dy, dz, live, a.sc, hi, lo);
+            ray_features(fx, fy, fz, dx, dy, dz, live, 0.0f, a.sc, hi, lo);
             tmem_st8(t_ahi + lane_base, hi);
             tmem_st8(t_alo + lane_base, lo);
             tc_wait_st();
