@@ -13,6 +13,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 using namespace rt;
@@ -476,16 +477,18 @@ static int launch_render(const rtiow_ctx* c, DeviceState& d, const rtiow_camera*
         int rc = prep_kernel(k, 0, 256, d.sms, &grid); if (rc) return rc;
         size_fetch(a, grid, 256);
         k<<<grid, 256, 0, st>>>(a);
-    } else if (sizeof(T) == 4 && use_tensor_scan(c, d)) {
+    } else if (use_tensor_scan(c, d)) {
         // sphere filter on the tensor cores: one CTA per SM (it owns all of TMEM), G groups of 128 rays + G issuer warps
-        using Shape = UmmaShape<RT_UMMA_GROUPS, RT_UMMA_CHUNK>;
-        auto k = render_kernel_umma<RT_UMMA_GROUPS, RT_UMMA_CHUNK>;
-        const size_t sm = Shape::smem_bytes(d.scene.u_npad);
-        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        grid = d.sms;
-        size_fetch(a, grid, Shape::kRayThreads);
-        k<<<grid, Shape::kThreads, sm, st>>>(reinterpret_cast<const RenderArgs<float>&>(a));
-        d.last_backend = RTIOW_SCAN_TENSOR;
+        if constexpr (std::is_same<T, float>::value) {
+            using Shape = UmmaShape<RT_UMMA_GROUPS, RT_UMMA_CHUNK>;
+            auto k = render_kernel_umma<RT_UMMA_GROUPS, RT_UMMA_CHUNK>;
+            const size_t sm = Shape::smem_bytes(d.scene.u_npad);
+            CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            grid = d.sms;
+            size_fetch(a, grid, Shape::kRayThreads);
+            k<<<grid, Shape::kThreads, sm, st>>>(a);
+            d.last_backend = RTIOW_SCAN_TENSOR;
+        }
     } else {
         const ScanCfg cfg = pick_cfg(d.scene.np);
         int min_ctas = 3;                                       // 3 CTAs x 256 threads x 80 registers fills the 64K-register file

@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(G * 160, 1) render_kernel_umma(const RenderArg
     UmmaCtx ux = umma_setup<G, NC>(smem_umma, a.scene, &tmem_base);
     const unsigned lane = threadIdx.x & 31u;
     if (ux.issuer_warp) {
-        if (lane == 0) umma_issuer<NC>(ux);
+        if (lane == 0) umma_issuer<G, NC>(ux);
     } else {
         const unsigned lt_mask = (1u << lane) - 1u;
         PathState<float> ps; init_path(ps);
@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(G * 160, 1) render_kernel_umma(const RenderArg
             pending = false;
 
             n_rays_w += __popc(__ballot_sync(RT_FULL, active));              // world.hit call count (main.rs:44)
-            const HitF h = closest_hit_umma<G, NC>(ux, a.scene, ps.o, ps.dhat, ps.tmin_n, ps.self_code, ps.self_n);
+            const HitF h = closest_hit_umma<G, NC, RT_UMMA_EW>(ux, a.scene, ps.o, ps.dhat, ps.tmin_n, ps.self_code, ps.self_n);
             if (active) {
                 if (h.idx < 0) accumulate(a, acc_lp, ps.thr * sky<float, true>(ps.dhat));                    // miss: sky (main.rs:54-56)
                 else { ps.o = ps.o + ps.dhat * h.t; hit_idx = h.idx; hit_code = h.code; pending = true; }    // ray.rs:15-17

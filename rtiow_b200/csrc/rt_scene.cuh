@@ -282,6 +282,30 @@ __device__ __noinline__ HitF big_spheres_hit(const double4* __restrict__ big, co
     return h;
 }
 
+// The same test with the result kept in f64 and no earlier hit to compare with: the tensor-core scan (rt_umma_scan.cuh) runs
+// it while the first MMA chunk is in flight and merges afterwards — (t ascending, list index descending) is a total order, so
+// the closest hit does not depend on the order in which candidates are offered.
+__device__ __noinline__ void big_spheres_best(const double4* __restrict__ big, const int* __restrict__ big_idx, int nb, V3<float> o, V3<float> dhat,
+                                              float t_min, int self_code, V3<float> self_n, double* t_out, int* idx_out, int* code_out)
+{
+    const V3<double> od = mk<double>(o.x, o.y, o.z), dd = mk<double>(dhat.x, dhat.y, dhat.z);
+    const double inv_ad = 2.0 - length_squared(dd);
+    double tbd = __longlong_as_double(0x7ff0000000000000LL); int ib = -1, code = RT_SELF_NONE;
+    for (int b = 0; b < nb; ++b) {
+        const double4 s = big[b];
+        const int before = ib; const double tbefore = tbd;
+        if (self_code == -2 - b) {
+            V3<double> sn = mk<double>(self_n.x, self_n.y, self_n.z);
+            sn = sn * (1.0 / sqrt(length_squared(sn)));
+            candidate_self<double>(dd, inv_ad, (double)t_min, sn, s.w, big_idx[b], &tbd, &ib);
+        } else {
+            candidate<double, true>(od, dd, inv_ad, (double)t_min, mk(s.x, s.y, s.z), s.w, big_idx[b], &tbd, &ib);
+        }
+        if (ib != before || tbd != tbefore) code = -2 - b;
+    }
+    *t_out = tbd; *idx_out = ib; *code_out = code;
+}
+
 // Closest hit of one ray against the whole scene: HittableList::hit (mod.rs:56-69).
 // float: packed filter over the small spheres + f64 test of the big ones; all lanes of the warp
 // must call together.  self_code / self_n identify the sphere the ray starts on (RT_SELF_NONE for

@@ -9,9 +9,12 @@
 //                   the sign bits into 32-sphere words ; survivors -> per-lane candidate list -> precise test
 //                   (sphere_roots, rt_device.cuh), exactly as the FP32 scan of rt_scene.cuh does.
 // The issuer is a warp of its own because tcgen05.mma issue stalls the issuing thread while the tensor pipe is busy
-// (tools/probe_umma_filter.cu: an issuer that shares a warp with an epilogue halves the throughput).  D is single-buffered
-// per group: while one group's MMAs run, the other groups collect signs, so the tensor pipe and the ALU pipe overlap
-// across groups (G = 4, NC = 64: 143.6 TFLOP/s-equivalent stand-alone against 65.8 for the FP32 filter).
+// (tools/probe_umma_filter.cu: an issuer that shares a warp with an epilogue halves the throughput), and every group has
+// its own: one thread polling all groups' barriers (mbarrier.test_wait) measured 40 % slower in situ.  D is single-buffered
+// per group: while one group's MMAs run, the other groups collect signs, so the tensor pipe and the ALU pipe overlap across
+// groups (stand-alone, G = 4, NC = 64: 143.6 TFLOP/s-equivalent against 65.8 for the FP32 filter).  The render kernel is
+// bound by the latency of its per-ray code, and every extra group hides more of it (G = 4 -> 6: +13 %), so G is as large
+// as TMEM allows: 6 x (64 + 16) = 480 of 512 columns.
 // Each CTA owns all 512 TMEM columns, so exactly one CTA may live on an SM: the launch asks for more than half of the
 // SM's shared memory.
 #pragma once
@@ -20,8 +23,15 @@
 
 namespace rt {
 
-#define RT_UMMA_GROUPS 4                      // ray groups per CTA in the product kernels (16 ray warps + 4 issuer warps = 640 threads)
-#define RT_UMMA_CHUNK 64                      // spheres per MMA chunk (TMEM: 4 x (64 + 16) = 320 of 512 columns)
+#ifndef RT_UMMA_GROUPS
+#define RT_UMMA_GROUPS 6                      // ray groups per CTA in the product kernels (24 ray warps + 6 issuer warps = 960 threads, 64 registers)
+#endif
+#ifndef RT_UMMA_CHUNK
+#define RT_UMMA_CHUNK 64                      // spheres per MMA chunk (TMEM: 6 x (64 + 16) = 480 of 512 columns)
+#endif
+#ifndef RT_UMMA_EW
+#define RT_UMMA_EW 1                          // 32-sphere words fetched from TMEM at a time (registers: 32 per word)
+#endif
 #define RT_UMMA_MIN_SMEM (120 * 1024)        // > half an SM's shared memory: one CTA per SM (each CTA allocates all of TMEM)
 
 template <int G, int NC> struct UmmaShape {
@@ -102,7 +112,7 @@ __device__ __forceinline__ UmmaCtx umma_setup(unsigned char* smem_raw, const Sce
 }
 
 // The group's MMA issuer: ONE thread.  Returns when the group's ray threads have called umma_group_quit.
-template <int NC>
+template <int G, int NC>
 __device__ __forceinline__ void umma_issuer(const UmmaCtx& ux)
 {
     using namespace umma;
@@ -143,10 +153,11 @@ __device__ __forceinline__ void umma_teardown(uint32_t tmem_base)
 
 // Closest hit of one ray against the whole scene — the tensor-core twin of closest_hit<kSmem> (rt_scene.cuh); every one of
 // the group's 128 ray threads must call together (lanes without a ray pass anything: their result is ignored).
-template <int G, int NC>
+template <int G, int NC, int EW = NC / 32>
 __device__ __forceinline__ HitF closest_hit_umma(UmmaCtx& ux, const SceneDev& sc, V3<float> o, V3<float> dhat, float t_min, int self_code, V3<float> self_n)
 {
     using namespace umma;
+    static_assert(EW >= 1 && (NC / 32) % EW == 0, "EW = 32-sphere words loaded from TMEM at a time");
     constexpr int kStride = UmmaShape<G, NC>::kRayThreads;
     const float inv_a = 2.0f - length_squared(dhat);           // 1/a for a = 1 + e, |e| < 1e-6
     float tb = __int_as_float(0x7f800000);                     // f64::INFINITY at main.rs:44
@@ -159,37 +170,58 @@ __device__ __forceinline__ HitF closest_hit_umma(UmmaCtx& ux, const SceneDev& sc
     f = f - dhat * (dot(f, dhat) * inv_a);
     const float sigma = sc.filter_sigma * (fabsf(o.x) + fabsf(o.y) + fabsf(o.z));     // covers the f32 error of a far origin's foot point
     const bool live = length_squared(f) < sc.filter_R2 + sigma;                        // a line that misses the bounding sphere hits nothing
-    uint32_t hi[8], lo[8];
-    ray_features(f.x, f.y, f.z, dhat.x, dhat.y, dhat.z, live, sigma, sc.u_sc, hi, lo);
-    tmem_st8(ux.t_a + ux.lane_base, hi);
-    tmem_st8(ux.t_a + 8u + ux.lane_base, lo);
+    {
+        uint32_t hi[8], lo[8];
+        ray_features(f.x, f.y, f.z, dhat.x, dhat.y, dhat.z, live, sigma, sc.u_sc, hi, lo);
+        tmem_st8(ux.t_a + ux.lane_base, hi);
+        tmem_st8(ux.t_a + 8u + ux.lane_base, lo);
+    }
     tc_wait_st();
     tc_fence_before();
     mbar_arrive(ux.bar_afull);
+
+    // the large spheres (f64, ~100 dependent instructions) while the first chunk's MMAs are in flight
+    double t_big = __longlong_as_double(0x7ff0000000000000LL); int i_big = -1, c_big = RT_SELF_NONE;
+    if (sc.nb > 0) big_spheres_best(sc.big, sc.big_idx, sc.nb, o, dhat, t_min, self_code, self_n, &t_big, &i_big, &c_big);
 
     int nc = 0;
     for (int c = 0; c < ux.n_chunks; ++c) {
         mbar_wait(ux.bar_full, ux.full_phase); ux.full_phase ^= 1u;
         tc_fence_after();
-        uint32_t v[NC / 32][32];
 #pragma unroll
-        for (int w = 0; w < NC / 32; ++w) tmem_ld32(ux.t_d + ux.lane_base + 32u * w, v[w]);
-        tc_wait_ld();
-        tc_fence_before();
-        __syncwarp();
-        if ((threadIdx.x & 31) == 0) mbar_arrive(ux.bar_empty);            // the issuer may overwrite D: the next chunk's MMAs overlap the sign collection
+        for (int w0 = 0; w0 < NC / 32; w0 += EW) {
+            uint32_t v[EW][32];
 #pragma unroll
-        for (int w = 0; w < NC / 32; ++w) {
-            unsigned m = 0;
+            for (int w = 0; w < EW; ++w) tmem_ld32(ux.t_d + ux.lane_base + 32u * (w0 + w), v[w]);
+            tc_wait_ld();
+            if (w0 + EW == NC / 32) {                                          // the chunk's last loads: hand D back to the issuer, whose
+                tc_fence_before();                                             // next MMAs then overlap the sign collection
+                __syncwarp();
+                if ((threadIdx.x & 31) == 0) mbar_arrive(ux.bar_empty);
+            }
+            // sign bits -> 32-sphere words.  SHF runs on the half-rate ALU pipe with a 4-cycle dependent latency, so every word is
+            // collected as two independent 16-bit chains and the words in flight are interleaved: 2 EW chains
+            unsigned mh[EW], ml[EW];
 #pragma unroll
-            for (int k = 0; k < 32; ++k) m = __funnelshift_l(v[w][k], m, 1);          // bit (31-k) = sign of sphere k's discriminant
-            unsigned pass = ~m;                                                       // set: the sphere passed the filter
-            while (pass) {
-                const int k = __clz(pass);
-                pass &= ~(0x80000000u >> k);
-                const int p = c * NC + w * 32 + k;
-                if (nc < RT_CAND_CAP) { ux.cand[nc * kStride] = (uint16_t)p; ++nc; }
-                else if (p != self_code) { const float4 s = sc.small[p]; candidate<float, true>(o, dhat, inv_a, t_min, mk(s.x, s.y, s.z), s.w, p, &tb, &pb); }
+            for (int w = 0; w < EW; ++w) { mh[w] = 0; ml[w] = 0; }
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+#pragma unroll
+                for (int w = 0; w < EW; ++w) {
+                    mh[w] = __funnelshift_l(v[w][k], mh[w], 1);                // spheres 0..15 of the word
+                    ml[w] = __funnelshift_l(v[w][16 + k], ml[w], 1);           // spheres 16..31
+                }
+            }
+#pragma unroll
+            for (int w = 0; w < EW; ++w) {
+                unsigned pass = ~__byte_perm(ml[w], mh[w], 0x5410);            // bit (31-k) set: sphere k of the word passed the filter
+                while (pass) {
+                    const int k = __clz(pass);
+                    pass &= ~(0x80000000u >> k);
+                    const int p = c * NC + (w0 + w) * 32 + k;
+                    if (nc < RT_CAND_CAP) { ux.cand[nc * kStride] = (uint16_t)p; ++nc; }
+                    else if (p != self_code) { const float4 s = sc.small[p]; candidate<float, true>(o, dhat, inv_a, t_min, mk(s.x, s.y, s.z), s.w, p, &tb, &pb); }
+                }
             }
         }
     }
@@ -201,7 +233,9 @@ __device__ __forceinline__ HitF closest_hit_umma(UmmaCtx& ux, const SceneDev& sc
         }
     }
     HitF h; h.t = tb; h.idx = pb >= 0 ? sc.small_idx[pb] : -1; h.code = pb;
-    if (sc.nb > 0) h = big_spheres_hit(sc.big, sc.big_idx, sc.nb, o, dhat, t_min, self_code, self_n, h);
+    // merge with the large spheres: t ascending, then list index descending (sphere.rs:29,31 + mod.rs:61-66), compared in f64 as
+    // big_spheres_hit does
+    if (i_big >= 0 && (t_big < (double)h.t || (t_big == (double)h.t && i_big > h.idx))) { h.t = (float)t_big; h.idx = i_big; h.code = c_big; }
     return h;
 }
 

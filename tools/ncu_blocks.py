@@ -28,6 +28,8 @@ src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-so
 rows = list(csv.reader(io.StringIO(src)))
 hdr = rows[1]; data = [r for r in rows[2:] if len(r) == len(hdr)]
 iex, ismp, iav = hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("Thread Instructions Executed")
+# non-inlined callees (big_spheres_hit, filter_tail) follow the kernel in ncu's listing: keep them, without line info
+lines += [(0, ("callee", 0), r[1].strip()) for r in data[len(lines):]]
 assert len(data) == len(lines), (len(data), len(lines))
 def cost(op): return 2 if op.split()[-1 if op.startswith("@") else 0].startswith(("FFMA2", "FADD2", "FMUL2")) or " FFMA2" in op[:14] else 1
 recs = []
@@ -35,7 +37,7 @@ for r, (addr, loc, text) in zip(data, lines):
     op = text.split()[1] if text.startswith("@") else text.split()[0]
     recs.append((addr, loc, op, int(r[iex]), int(r[ismp]), int(r[iav]), 2 if op in ("FFMA2", "FADD2", "FMUL2") else 1))
 tot_cycles = sum(x[3] * x[6] for x in recs); tot_s = sum(x[4] for x in recs)
-scan_exec = max(x[3] for x in recs if x[2] == "FFMA2")          # executions of the scan's inner instructions
+scan_exec = max(x[3] for x in recs if x[2].split(".")[0] in ("FFMA2", "SHF"))    # executions of the scan's inner instructions (FFMA2 filter / SHF sign collection)
 n_ffma2 = sum(1 for x in recs if x[2] == "FFMA2" and x[3] > scan_exec // 2)
 words = 1
 print(f"# {rep}: {len(recs)} SASS instructions, issue-cycle model total {tot_cycles/1e9:.2f} G; per-'scan word' counts = executions / {scan_exec}")

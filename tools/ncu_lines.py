@@ -27,6 +27,7 @@ src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-so
 rows = list(csv.reader(io.StringIO(src)))
 hdr = rows[1]; data = [r for r in rows[2:] if len(r) == len(hdr)]
 iex, ismp, iav = hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("Thread Instructions Executed")
+lines += [(0, ("callee", 0), r[1].strip()) for r in data[len(lines):]]
 if len(data) != len(lines):
     print(f"WARNING: ncu has {len(data)} SASS instructions, nvdisasm {len(lines)}: is the .so the profiled build?")
 agg = collections.defaultdict(lambda: [0, 0, 0])
