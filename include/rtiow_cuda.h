@@ -89,8 +89,17 @@ typedef struct {
     uint32_t tile_rows;           /* rows per interleaved tile when the frame is split across GPUs (>=1) */
 } rtiow_params;
 
+/* How the row tiles of a multi-GPU frame reach rank 0 (the reference's collect(), main.rs:139).
+ * NCCL : equal-size (padded) tile buffers + ONE ncclAllGather per frame + a de-interleave kernel.
+ * FUSED: every rank's epilogue stores its pixels straight into their top-down place in rank 0's frame through NVLink peer
+ *        memory (cudaDeviceEnablePeerAccess inside one process, a CUDA IPC mapping across processes); across processes a
+ *        1-int ncclAllReduce is the frame-complete barrier.  No tile buffer, no de-interleave pass.
+ * AUTO : FUSED when the mapping is possible, else NCCL.  All three give the same bytes. */
+typedef enum { RTIOW_GATHER_AUTO = 0, RTIOW_GATHER_NCCL = 1, RTIOW_GATHER_FUSED = 2 } rtiow_gather_mode;
+#define RTIOW_NCCL_UNIQUE_ID_BYTES 128
+
 typedef struct {
-    double   kernel_ms;           /* CUDA-event time of the render kernels on device 0 / this rank */
+    double   kernel_ms;           /* CUDA-event time of the render kernels: this rank, or the slowest device of an n-GPU ctx */
     double   total_ms;            /* host wall time of the call */
     uint64_t paths;               /* width*height*spp handled by this call */
     uint64_t rays_traced;         /* exact count of world.hit calls (main.rs:44) */
@@ -118,6 +127,17 @@ void rtiow_ctx_destroy(rtiow_ctx* ctx);
  * scene that does not qualify makes those calls return RTIOW_ERR_UNSUPPORTED (never a silent fallback). */
 int  rtiow_ctx_set_scan_backend(rtiow_ctx* ctx, int backend);
 
+/* One process per GPU (MPI / torchrun style) with the gather INSIDE the library.  Rank 0 calls rtiow_nccl_unique_id and hands
+ * the RTIOW_NCCL_UNIQUE_ID_BYTES bytes to every rank by any means (MPI_Bcast, a file, torch.distributed); every rank then
+ * calls rtiow_ctx_create_rank (collective: ncclCommInitRank).  world = 1 needs no id and no NCCL.  NCCL is loaded at run time
+ * (libnccl.so.2); if it is missing these return RTIOW_ERR_NCCL. */
+int  rtiow_nccl_unique_id(void* out_id);
+int  rtiow_ctx_create_rank(int device, int rank, int world, const void* nccl_unique_id, rtiow_ctx** out);
+/* rtiow_gather_mode of every later multi-GPU render on this ctx (an n-GPU ctx or a rank ctx) */
+int  rtiow_ctx_set_gather(rtiow_ctx* ctx, int mode);
+/* one line describing the gather the last render used (for logs and bench lines) */
+int  rtiow_ctx_gather_info(rtiow_ctx* ctx, char* buf, size_t n);
+
 /* Replaces building `world` for the GPU (main.rs:62-99 push calls): validates, converts to the
  * device SoA and uploads to every device of the ctx.  May be called again to replace the scene. */
 int rtiow_scene_upload(rtiow_ctx* ctx, const rtiow_spheres* spheres, const rtiow_materials* materials);
@@ -142,7 +162,16 @@ typedef int (*rtiow_progress_fn)(void* user, uint32_t pass, uint32_t n_passes, u
 int rtiow_render_progressive(rtiow_ctx* ctx, const rtiow_camera* cam, const rtiow_params* p, uint32_t n_passes,
                              rtiow_progress_fn on_pass, void* user, uint8_t* out_rgba, rtiow_stats* stats);
 
-/* --- one-process-per-GPU pieces (rank r of world G renders rows {y : (y / tile_rows) % G == r}) ---- */
+/* The drop-in call of a rank ctx (collective: every rank calls it with the same camera and params).  Renders this rank's rows
+ * {y : (y / tile_rows) % world == rank}, gathers inside the library, and writes the whole top-down RGBA8 frame into out_rgba
+ * (HOST memory) on rank 0 — and on every rank that passes a buffer when the gather is NCCL.  out_rgba may be NULL on ranks > 0.
+ * stats describe this rank (paths, rays, kernel_ms of its own rows). */
+int rtiow_render_rank(rtiow_ctx* ctx, const rtiow_camera* cam, const rtiow_params* p, uint8_t* out_rgba, rtiow_stats* stats);
+/* the same, leaving the frame in DEVICE memory: *d_frame = the whole frame on rank 0 (NCCL gather: on every rank; FUSED: NULL
+ * on ranks > 0), owned by the ctx and valid until its next render. */
+int rtiow_render_rank_device(rtiow_ctx* ctx, const rtiow_camera* cam, const rtiow_params* p, const void** d_frame, rtiow_stats* stats);
+
+/* --- lower-level one-process-per-GPU pieces for callers that own the gather (rank r of world G renders rows {y : (y / tile_rows) % G == r}) ---- */
 /* bytes of one rank's tile buffer (equal on every rank; padded when the tile count does not divide) */
 int rtiow_tile_buffer_bytes(const rtiow_params* p, int world, size_t* out_bytes);
 /* render this rank's tiles into DEVICE memory d_tiles (>= rtiow_tile_buffer_bytes), rank-local

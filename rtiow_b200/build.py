@@ -56,7 +56,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
     env = dict(os.environ)
     env.pop("CC", None), env.pop("CXX", None)      # the image exports a wrapper gcc that lacks specs
     extra = os.environ.get("RTIOW_NVCC_EXTRA", "").split()        # experiments only (tools/): e.g. -DRT_FLUSH_PER_PATH=1
-    cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-shared", "-ccbin", "/usr/bin/g++", "-o", str(LIB), *map(str, srcs)]
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-shared", "-ccbin", "/usr/bin/g++", "-o", str(LIB), *map(str, srcs), "-ldl"]      # NCCL is dlopen()ed on first multi-GPU use
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True, env=env)

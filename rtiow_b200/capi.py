@@ -18,6 +18,8 @@ MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC = 0, 1, 2
 F32, F64 = 0, 1
 ABI_VERSION = 3
 SCAN_AUTO, SCAN_FP32, SCAN_TENSOR = 0, 1, 2
+GATHER_AUTO, GATHER_NCCL, GATHER_FUSED = 0, 1, 2
+NCCL_UNIQUE_ID_BYTES = 128
 
 _STATUS = {OK: "OK", ERR_INVALID_ARG: "INVALID_ARG", ERR_UNSUPPORTED: "UNSUPPORTED", ERR_CUDA: "CUDA", ERR_NCCL: "NCCL",
            ERR_NO_DEVICE: "NO_DEVICE", ERR_NOMEM: "NOMEM", ERR_CANCELLED: "CANCELLED"}
@@ -27,7 +29,8 @@ PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint3
 # every symbol include/rtiow_cuda.h declares (tests check the .so exports exactly these)
 SYMBOLS = [
     "rtiow_abi_version", "rtiow_last_error", "rtiow_device_count", "rtiow_ctx_create", "rtiow_ctx_create_on_device",
-    "rtiow_ctx_destroy", "rtiow_ctx_set_scan_backend", "rtiow_scene_upload", "rtiow_camera_new", "rtiow_params_default", "rtiow_render", "rtiow_render_progressive",
+    "rtiow_ctx_destroy", "rtiow_ctx_set_scan_backend", "rtiow_nccl_unique_id", "rtiow_ctx_create_rank", "rtiow_ctx_set_gather",
+    "rtiow_ctx_gather_info", "rtiow_render_rank", "rtiow_render_rank_device", "rtiow_scene_upload", "rtiow_camera_new", "rtiow_params_default", "rtiow_render", "rtiow_render_progressive",
     "rtiow_tile_buffer_bytes", "rtiow_render_tiles_device", "rtiow_render_to_frame_device", "rtiow_deinterleave_device", "rtiow_sphere_hit_batch",
     "rtiow_hitlist_batch", "rtiow_scatter_batch", "rtiow_get_ray_batch", "rtiow_to_rgba_batch", "rtiow_reflect_batch",
     "rtiow_refract_batch", "rtiow_ray_color_batch", "rtiow_ray_color_trace_batch", "rtiow_sampler_batch", "rtiow_fp32_peak_probe", "rtiow_flush_l2",
@@ -105,6 +108,12 @@ def _declare(L):
         "rtiow_ctx_create_on_device": (C.c_int, [C.c_int, C.POINTER(P)]),
         "rtiow_ctx_destroy": (None, [P]),
         "rtiow_ctx_set_scan_backend": (C.c_int, [P, C.c_int]),
+        "rtiow_nccl_unique_id": (C.c_int, [P]),
+        "rtiow_ctx_create_rank": (C.c_int, [C.c_int, C.c_int, C.c_int, P, C.POINTER(P)]),
+        "rtiow_ctx_set_gather": (C.c_int, [P, C.c_int]),
+        "rtiow_ctx_gather_info": (C.c_int, [P, C.c_char_p, C.c_size_t]),
+        "rtiow_render_rank": (C.c_int, [P, C.POINTER(Camera), C.POINTER(Params), P, C.POINTER(Stats)]),
+        "rtiow_render_rank_device": (C.c_int, [P, C.POINTER(Camera), C.POINTER(Params), C.POINTER(P), C.POINTER(Stats)]),
         "rtiow_scene_upload": (C.c_int, [P, C.POINTER(Spheres), C.POINTER(Materials)]),
         "rtiow_camera_new": (C.c_int, [P, P, P, d, d, d, d, C.POINTER(Camera)]),
         "rtiow_params_default": (None, [C.POINTER(Params)]),
@@ -183,17 +192,34 @@ def random_scene(seed: int = 1, half_extent: int = 11, material_mode: int = 0):
                 mat_kind=kind[:k].copy(), mat_albedo=alb[:k].copy(), mat_param=prm[:k].copy())
 
 
-class Context:
-    """rtiow_ctx: owns device buffers and streams.  Single caller (Send, !Sync)."""
+def nccl_unique_id() -> bytes:
+    """rank 0: the 128 bytes every rank passes to Context(rank=..., world=..., nccl_id=...) (MPI_Bcast / a file / torch.distributed)"""
+    buf = C.create_string_buffer(NCCL_UNIQUE_ID_BYTES)
+    _check(lib().rtiow_nccl_unique_id(buf))
+    return buf.raw
 
-    def __init__(self, n_gpus: int = 1, device: int | None = None):
+
+class Context:
+    """rtiow_ctx: owns device buffers and streams.  Single caller (Send, !Sync).
+
+    Context(n)                                  one process driving GPUs 0..n-1 (rtiow_ctx_create)
+    Context(device=d)                           this process drives GPU d only; the caller owns any gather (rtiow_ctx_create_on_device)
+    Context(device=d, rank=r, world=w, nccl_id) one process per GPU with the gather inside the library (rtiow_ctx_create_rank)
+    """
+
+    def __init__(self, n_gpus: int = 1, device: int | None = None, rank: int | None = None, world: int = 1, nccl_id: bytes | None = None):
         h = C.c_void_p()
-        if device is None:
+        if rank is not None:
+            if world > 1 and (nccl_id is None or len(nccl_id) != NCCL_UNIQUE_ID_BYTES):
+                raise ValueError("nccl_id must be the 128 bytes of rank 0's nccl_unique_id()")
+            _check(lib().rtiow_ctx_create_rank(0 if device is None else device, rank, world, nccl_id, C.byref(h)))
+        elif device is None:
             _check(lib().rtiow_ctx_create(n_gpus, C.byref(h)))
         else:
             _check(lib().rtiow_ctx_create_on_device(device, C.byref(h)))
         self._h = h
         self.n_spheres = 0
+        self.rank, self.world = (rank or 0), world
 
     def close(self):
         if getattr(self, "_h", None):
@@ -203,6 +229,31 @@ class Context:
     def set_scan_backend(self, backend: int):
         """SCAN_AUTO / SCAN_FP32 (FFMA2 filter on the CUDA cores) / SCAN_TENSOR (tcgen05 filter): same hits, same images."""
         _check(lib().rtiow_ctx_set_scan_backend(self._h, backend))
+
+    def set_gather(self, mode: int):
+        """GATHER_AUTO / GATHER_NCCL (tile buffers + ncclAllGather + de-interleave) / GATHER_FUSED (peer stores into rank 0's frame)"""
+        _check(lib().rtiow_ctx_set_gather(self._h, mode))
+
+    def gather_info(self) -> str:
+        buf = C.create_string_buffer(512)
+        _check(lib().rtiow_ctx_gather_info(self._h, buf, 512))
+        return buf.value.decode()
+
+    def render_rank(self, cam: Camera, params: Params, out: np.ndarray | None = None, want_frame: bool | None = None):
+        """rtiow_render_rank (collective).  Rank 0 (or want_frame=True under the NCCL gather) receives the whole frame in host memory."""
+        if want_frame is None:
+            want_frame = self.rank == 0
+        if want_frame and out is None:
+            out = np.empty((params.height, params.width, 4), np.uint8)
+        st = Stats()
+        _check(lib().rtiow_render_rank(self._h, C.byref(cam), C.byref(params), _p(out) if want_frame else None, C.byref(st)))
+        return (out if want_frame else None), st.as_dict()
+
+    def render_rank_device(self, cam: Camera, params: Params):
+        """rtiow_render_rank_device (collective): -> (device pointer of the whole frame or 0, stats)"""
+        st = Stats(); ptr = C.c_void_p()
+        _check(lib().rtiow_render_rank_device(self._h, C.byref(cam), C.byref(params), C.byref(ptr), C.byref(st)))
+        return (ptr.value or 0), st.as_dict()
 
     def __del__(self):
         try:

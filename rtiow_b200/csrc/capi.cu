@@ -5,6 +5,9 @@
 #include "../../include/rtiow_cuda.h"
 #include "rt_unit.cuh"
 
+#include <nccl.h>
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -93,6 +96,20 @@ struct rtiow_ctx {
     int scan_backend = RTIOW_SCAN_AUTO;  // rtiow_ctx_set_scan_backend
     size_t scene_bytes = 0;
     bool peer_ok = true;                 // every device can store into device 0's memory (NVLink P2P): fused epilogue + gather
+    // the gather of the row tiles (rtiow_ctx_set_gather)
+    int gather = RTIOW_GATHER_AUTO;
+    std::vector<ncclComm_t> comms;       // one process driving n GPUs: ncclCommInitAll, created on first use
+    // one process per GPU (rtiow_ctx_create_rank)
+    int rank = 0, world = 1;
+    ncclComm_t comm = nullptr;
+    int* d_flag = nullptr;               // 1-int all-reduce: the frame-complete barrier of the fused gather / agreement votes
+    // fused gather across processes: rank 0's double-buffered frame, mapped into every rank through CUDA IPC
+    uint32_t* ipc_frame = nullptr; size_t ipc_frame_px = 0; bool ipc_owner = false; int ipc_state = 0;   // 0 untried, 1 mapped, -1 unavailable
+    uint32_t ipc_parity = 0;
+    // NCCL user-buffer registration of the tile / gathered buffers (symmetric window), when the library offers it
+    void* win_tiles = nullptr; void* win_gathered = nullptr; uint32_t* nccl_tiles = nullptr; uint32_t* nccl_gathered = nullptr; size_t nccl_tile_px = 0;
+    bool windows_registered = false;
+    std::string gather_note;
 };
 
 static int init_device(DeviceState& d, int device)
@@ -157,9 +174,129 @@ extern "C" int rtiow_ctx_set_scan_backend(rtiow_ctx* c, int backend)
     return RTIOW_OK;
 }
 
+extern "C" void rtiow_ctx_destroy(rtiow_ctx* c);
+// ------------------------------------------------------------------------------------------------
+// NCCL, loaded at run time (dlopen): a single-GPU caller needs no NCCL at all, and a process that already carries one (the
+// bench under torchrun: torch's bundled libnccl.so.2) shares it instead of mapping a second copy with the same soname.
+// ------------------------------------------------------------------------------------------------
+struct NcclApi {
+    void* h = nullptr; int version = 0;
+    ncclResult_t (*GetVersion)(int*) = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    // optional (NCCL >= 2.27): user buffers registered as a symmetric window
+    ncclResult_t (*MemAlloc)(void**, size_t) = nullptr;
+    ncclResult_t (*MemFree)(void*) = nullptr;
+    ncclResult_t (*CommWindowRegister)(ncclComm_t, void*, size_t, ncclWindow_t*, int) = nullptr;
+    ncclResult_t (*CommWindowDeregister)(ncclComm_t, ncclWindow_t) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load()
+{
+    if (g_nccl.h) return RTIOW_OK;
+    void* h = nullptr;
+    const char* tried = "libnccl.so.2, libnccl.so";
+    if (const char* p = getenv("RTIOW_NCCL_LIB")) { h = dlopen(p, RTLD_NOW | RTLD_GLOBAL); tried = p; }     // deployment knob: which NCCL to load
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return fail(RTIOW_ERR_NCCL, "NCCL is not available (%s): %s — multi-GPU gathers need it, single-GPU rendering does not", tried, dlerror());
+    NcclApi a; a.h = h;
+#define SYM(field, name) *(void**)(&a.field) = dlsym(h, name)
+    SYM(GetVersion, "ncclGetVersion"); SYM(GetUniqueId, "ncclGetUniqueId"); SYM(CommInitRank, "ncclCommInitRank"); SYM(CommInitAll, "ncclCommInitAll");
+    SYM(CommDestroy, "ncclCommDestroy"); SYM(AllGather, "ncclAllGather"); SYM(AllReduce, "ncclAllReduce"); SYM(Broadcast, "ncclBroadcast");
+    SYM(GroupStart, "ncclGroupStart"); SYM(GroupEnd, "ncclGroupEnd"); SYM(GetErrorString, "ncclGetErrorString");
+    SYM(MemAlloc, "ncclMemAlloc"); SYM(MemFree, "ncclMemFree"); SYM(CommWindowRegister, "ncclCommWindowRegister"); SYM(CommWindowDeregister, "ncclCommWindowDeregister");
+#undef SYM
+    if (!a.GetVersion || !a.GetUniqueId || !a.CommInitRank || !a.CommInitAll || !a.CommDestroy || !a.AllGather || !a.AllReduce || !a.Broadcast ||
+        !a.GroupStart || !a.GroupEnd || !a.GetErrorString)
+        return fail(RTIOW_ERR_NCCL, "the NCCL library that was loaded lacks a required symbol");
+    a.GetVersion(&a.version);
+    g_nccl = a;
+    return RTIOW_OK;
+}
+#define NC(call)                                                                                         \
+    do {                                                                                                 \
+        ncclResult_t r_ = (call);                                                                        \
+        if (r_ != ncclSuccess) return fail(RTIOW_ERR_NCCL, "%s -> %s (%s:%d)", #call, g_nccl.GetErrorString(r_), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" int rtiow_nccl_unique_id(void* out_id)
+{
+    if (!out_id) return fail(RTIOW_ERR_INVALID_ARG, "out_id is NULL");
+    static_assert(sizeof(ncclUniqueId) == RTIOW_NCCL_UNIQUE_ID_BYTES, "ncclUniqueId is 128 bytes");
+    int rc = nccl_load(); if (rc) return rc;
+    ncclUniqueId id;
+    NC(g_nccl.GetUniqueId(&id));
+    memcpy(out_id, &id, sizeof id);
+    return RTIOW_OK;
+}
+
+extern "C" int rtiow_ctx_create_rank(int device, int rank, int world, const void* nccl_unique_id, rtiow_ctx** out)
+{
+    if (!out) return fail(RTIOW_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    if (world < 1 || rank < 0 || rank >= world) return fail(RTIOW_ERR_INVALID_ARG, "bad rank/world (%d of %d)", rank, world);
+    if (world > 1 && !nccl_unique_id) return fail(RTIOW_ERR_INVALID_ARG, "nccl_unique_id is NULL (rank 0 calls rtiow_nccl_unique_id and hands the 128 bytes to every rank)");
+    rtiow_ctx* c = nullptr;
+    int rc = create_ctx(std::vector<int>{ device }, &c); if (rc) return rc;
+    c->rank = rank; c->world = world;
+    if (world > 1) {
+        rc = nccl_load(); if (rc) { rtiow_ctx_destroy(c); return rc; }
+        ncclUniqueId id; memcpy(&id, nccl_unique_id, sizeof id);
+        cudaSetDevice(device);
+        ncclResult_t r = g_nccl.CommInitRank(&c->comm, world, id, rank);
+        if (r != ncclSuccess) { c->comm = nullptr; rtiow_ctx_destroy(c); return fail(RTIOW_ERR_NCCL, "ncclCommInitRank(rank %d of %d) -> %s", rank, world, g_nccl.GetErrorString(r)); }
+        if (cudaMalloc(&c->d_flag, 2 * sizeof(int)) != cudaSuccess) { rtiow_ctx_destroy(c); return fail(RTIOW_ERR_NOMEM, "cudaMalloc of the barrier flag failed"); }
+    }
+    *out = c;
+    return RTIOW_OK;
+}
+
+extern "C" int rtiow_ctx_set_gather(rtiow_ctx* c, int mode)
+{
+    if (!c) return fail(RTIOW_ERR_INVALID_ARG, "ctx is NULL");
+    if (mode != RTIOW_GATHER_AUTO && mode != RTIOW_GATHER_NCCL && mode != RTIOW_GATHER_FUSED) return fail(RTIOW_ERR_INVALID_ARG, "unknown gather mode %d", mode);
+    c->gather = mode;
+    return RTIOW_OK;
+}
+
+extern "C" int rtiow_ctx_gather_info(rtiow_ctx* c, char* buf, size_t n)
+{
+    if (!c || !buf || n == 0) return fail(RTIOW_ERR_INVALID_ARG, "NULL argument");
+    snprintf(buf, n, "%s", c->gather_note.empty() ? "single GPU: no gather" : c->gather_note.c_str());
+    return RTIOW_OK;
+}
+
+static void release_gather(rtiow_ctx* c)
+{
+    if (c->dev.empty()) return;
+    cudaSetDevice(c->dev[0].device);
+    if (c->windows_registered && g_nccl.CommWindowDeregister && c->comm) {
+        if (c->win_tiles) g_nccl.CommWindowDeregister(c->comm, (ncclWindow_t)c->win_tiles);
+        if (c->win_gathered) g_nccl.CommWindowDeregister(c->comm, (ncclWindow_t)c->win_gathered);
+    }
+    if (c->nccl_tiles && g_nccl.MemFree) g_nccl.MemFree(c->nccl_tiles);
+    if (c->nccl_gathered && g_nccl.MemFree) g_nccl.MemFree(c->nccl_gathered);
+    if (c->ipc_frame) { if (c->ipc_owner) cudaFree(c->ipc_frame); else cudaIpcCloseMemHandle(c->ipc_frame); }
+    if (c->d_flag) cudaFree(c->d_flag);
+    if (c->comm) g_nccl.CommDestroy(c->comm);
+    for (size_t i = 0; i < c->comms.size(); ++i) { cudaSetDevice(c->dev[i].device); if (c->comms[i]) g_nccl.CommDestroy(c->comms[i]); }
+    c->comms.clear(); c->comm = nullptr; c->d_flag = nullptr; c->ipc_frame = nullptr; c->nccl_tiles = c->nccl_gathered = nullptr;
+}
+
 extern "C" void rtiow_ctx_destroy(rtiow_ctx* c)
 {
     if (!c) return;
+    for (auto& d : c->dev) { cudaSetDevice(d.device); if (d.stream) cudaStreamSynchronize(d.stream); }
+    release_gather(c);
     for (auto& d : c->dev) {
         cudaSetDevice(d.device);
         if (d.stream) cudaStreamSynchronize(d.stream);
@@ -641,35 +778,62 @@ static int render_frame(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_param
         CU(cudaEventRecord(d0.ev1, d0.stream));
         d_final = d0.tiles.p;                                  // world == 1: rank-local order IS top-down
     } else {
-        // interleaved row tiles on every GPU.  With NVLink peer access (every B200 box) each rank's epilogue stores its
-        // pixels straight into device 0's top-down frame (finalize_to_frame_kernel): compute and gather are one kernel,
-        // nothing is staged.  Without peer access: tile buffers + cudaMemcpyPeerAsync + de-interleave.
+        // interleaved row tiles on every GPU.  Three gathers:
+        //   fused (default with NVLink peer access, every B200 box): each rank's epilogue stores its pixels straight into device
+        //     0's top-down frame (finalize_to_frame_kernel): compute and gather are one kernel, nothing is staged;
+        //   NCCL (rtiow_ctx_set_gather(RTIOW_GATHER_NCCL)): ncclCommInitAll once, then per frame one grouped
+        //     ncclAllGather of the equal-size (padded) tile buffers + the de-interleave kernel on device 0;
+        //   without peer access and without NCCL: tile buffers + cudaMemcpyPeerAsync + de-interleave.
+        const bool use_nccl = c->gather == RTIOW_GATHER_NCCL;
+        if (c->gather == RTIOW_GATHER_FUSED && !c->peer_ok) return fail(RTIOW_ERR_UNSUPPORTED, "RTIOW_GATHER_FUSED needs peer access from every device to device 0");
+        const bool fused = !use_nccl && c->peer_ok;
+        if (use_nccl && c->comms.empty()) {
+            rc = nccl_load(); if (rc) return rc;
+            std::vector<int> devs; for (auto& d : c->dev) devs.push_back(d.device);
+            c->comms.assign(world, nullptr);
+            ncclResult_t r = g_nccl.CommInitAll(c->comms.data(), (int)world, devs.data());
+            if (r != ncclSuccess) { c->comms.clear(); return fail(RTIOW_ERR_NCCL, "ncclCommInitAll(%u devices) -> %s", world, g_nccl.GetErrorString(r)); }
+        }
         CU(d0.frame.resize((size_t)p->width * p->height));
-        if (!c->peer_ok) CU(d0.gathered.resize(tile_px * world));
+        if (!fused) CU(d0.gathered.resize(tile_px * world));
         for (uint32_t r = 0; r < world; ++r) {
             DeviceState& d = c->dev[r];
             CU(cudaSetDevice(d.device));
             uint32_t* dst = nullptr;
-            if (!c->peer_ok) { if (r == 0) dst = d0.gathered.p; else { CU(d.tiles.resize(tile_px)); dst = d.tiles.p; } }
-            if (r == 0) CU(cudaEventRecord(d.ev0, d.stream));
-            rc = render_tiles(c, d, cam, p, r, world, dst, d.stream, &launches, c->peer_ok ? d0.frame.p : nullptr, &sr); if (rc) return rc;
-            if (r == 0) CU(cudaEventRecord(d.ev1, d.stream));
-            if (r != 0) {
-                if (!c->peer_ok) {
+            if (use_nccl) { CU(d.tiles.resize(tile_px)); CU(d.gathered.resize(tile_px * world)); dst = d.tiles.p; }
+            else if (!fused) { if (r == 0) dst = d0.gathered.p; else { CU(d.tiles.resize(tile_px)); dst = d.tiles.p; } }
+            CU(cudaEventRecord(d.ev0, d.stream));
+            rc = render_tiles(c, d, cam, p, r, world, dst, d.stream, &launches, fused ? d0.frame.p : nullptr, &sr); if (rc) return rc;
+            CU(cudaEventRecord(d.ev1, d.stream));
+            if (r != 0 && !use_nccl) {
+                if (!fused) {
                     const size_t bytes = (size_t)rows_of_rank(p->height, p->tile_rows, world, r) * p->width * 4;
                     CU(cudaMemcpyPeerAsync(d0.gathered.p + tile_px * r, d0.device, d.tiles.p, d.device, bytes, d.stream));
                 }
                 CU(cudaEventRecord(d.ev_done, d.stream));
             }
         }
+        if (use_nccl) {
+            NC(g_nccl.GroupStart());
+            for (uint32_t r = 0; r < world; ++r) {
+                DeviceState& d = c->dev[r];
+                ncclResult_t e = g_nccl.AllGather(d.tiles.p, d.gathered.p, tile_px * 4, ncclUint8, c->comms[r], d.stream);
+                if (e != ncclSuccess) { g_nccl.GroupEnd(); return fail(RTIOW_ERR_NCCL, "ncclAllGather(rank %u) -> %s", r, g_nccl.GetErrorString(e)); }
+            }
+            NC(g_nccl.GroupEnd());
+        }
         CU(cudaSetDevice(d0.device));
-        for (uint32_t r = 1; r < world; ++r) CU(cudaStreamWaitEvent(d0.stream, c->dev[r].ev_done, 0));
-        if (!c->peer_ok) {
+        if (!use_nccl) for (uint32_t r = 1; r < world; ++r) CU(cudaStreamWaitEvent(d0.stream, c->dev[r].ev_done, 0));
+        if (!fused) {
             const size_t npx = (size_t)p->width * p->height;
             deinterleave_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, d0.stream>>>(d0.gathered.p, p->width, p->height, p->tile_rows, world, tile_px, d0.frame.p);
             CU(cudaGetLastError());
             ++launches;
         }
+        char note[160];
+        snprintf(note, sizeof note, "one process, %u GPUs: %s", world, fused ? "epilogue stores into device 0's frame over NVLink peer memory (fused gather)"
+                 : use_nccl ? "tile buffers + grouped ncclAllGather (ncclCommInitAll) + de-interleave" : "tile buffers + cudaMemcpyPeerAsync + de-interleave");
+        c->gather_note = note;
         d_final = d0.frame.p;
     }
     CU(cudaMemcpyAsync(d0.pinned, d_final, frame_bytes, cudaMemcpyDeviceToHost, d0.stream));
@@ -686,6 +850,7 @@ static int render_frame(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_param
             CU(cudaMemcpyAsync(d.pinned_cnt, d.counters.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.stream));
             CU(cudaStreamSynchronize(d.stream));
             rays += d.pinned_cnt[1];
+            float mr = 0; CU(cudaEventElapsedTime(&mr, d.ev0, d.ev1)); ms = std::max(ms, mr);          // the slowest device's kernels
         }
         stats->kernel_ms = ms; stats->total_ms = now_ms() - t0;
         stats->paths = (uint64_t)p->width * p->height * sr.count;
@@ -733,6 +898,197 @@ extern "C" int rtiow_render_progressive(rtiow_ctx* c, const rtiow_camera* cam, c
     total.total_ms = now_ms() - t0;
     if (stats) *stats = total;
     return RTIOW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one process per GPU (rtiow_ctx_create_rank): render this rank's row tiles and gather INSIDE the library.  The reference's
+// gather is collect() at main.rs:139 (rows are the unit of work, main.rs:122-123).
+// ------------------------------------------------------------------------------------------------
+// 1-int all-reduce, stream-ordered after whatever each rank enqueued before it: when it completes on a rank, every rank's
+// earlier work on its stream — the peer stores of its epilogue included — has completed
+static int nccl_barrier(rtiow_ctx* c, cudaStream_t st)
+{
+    NC(g_nccl.AllReduce(c->d_flag, c->d_flag + 1, 1, ncclInt32, ncclSum, c->comm, st));
+    return RTIOW_OK;
+}
+// min over ranks of a host value (agreement votes; synchronises the stream)
+static int nccl_vote_min(rtiow_ctx* c, int mine, int* all, cudaStream_t st)
+{
+    CU(cudaMemcpyAsync(c->d_flag, &mine, sizeof(int), cudaMemcpyHostToDevice, st));
+    NC(g_nccl.AllReduce(c->d_flag, c->d_flag + 1, 1, ncclInt32, ncclMin, c->comm, st));
+    CU(cudaMemcpyAsync(all, c->d_flag + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return RTIOW_OK;
+}
+
+// The fused gather across processes: rank 0 owns a double-buffered top-down frame; its CUDA IPC handle travels to the other
+// ranks in an ncclBroadcast and they map it (NVLink peer memory).  Collective: every rank calls it with the same frame size.
+static int ensure_ipc_frame(rtiow_ctx* c, size_t npx, cudaStream_t st)
+{
+    if (c->ipc_state == -1 || (c->ipc_state == 1 && c->ipc_frame_px == npx)) return RTIOW_OK;
+    CU(cudaStreamSynchronize(st));
+    if (c->ipc_frame) { if (c->ipc_owner) cudaFree(c->ipc_frame); else cudaIpcCloseMemHandle(c->ipc_frame); c->ipc_frame = nullptr; }
+    int ok = 1;
+    cudaIpcMemHandle_t h; memset(&h, 0, sizeof h);
+    if (c->rank == 0) {
+        if (cudaMalloc(&c->ipc_frame, 2 * npx * sizeof(uint32_t)) != cudaSuccess) { cudaGetLastError(); c->ipc_frame = nullptr; ok = 0; }
+        else if (cudaIpcGetMemHandle(&h, c->ipc_frame) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+        c->ipc_owner = true;
+    }
+    unsigned char* d_h = nullptr;
+    CU(cudaMalloc(&d_h, sizeof h));
+    cudaMemcpyAsync(d_h, &h, sizeof h, cudaMemcpyHostToDevice, st);
+    ncclResult_t r = g_nccl.Broadcast(d_h, d_h, sizeof h, ncclUint8, 0, c->comm, st);
+    cudaMemcpyAsync(&h, d_h, sizeof h, cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(d_h);
+    if (r != ncclSuccess) return fail(RTIOW_ERR_NCCL, "ncclBroadcast(IPC handle) -> %s", g_nccl.GetErrorString(r));
+    if (e != cudaSuccess) return fail(RTIOW_ERR_CUDA, "IPC handle exchange -> %s", cudaGetErrorString(e));
+    if (c->rank != 0) {
+        c->ipc_owner = false;
+        if (cudaIpcOpenMemHandle((void**)&c->ipc_frame, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); c->ipc_frame = nullptr; ok = 0; }
+    }
+    int all = 0;
+    int rc = nccl_vote_min(c, ok, &all, st); if (rc) return rc;
+    if (!all) {         // some rank could not map the frame (no peer access / IPC across containers): every rank falls back together
+        if (c->ipc_frame) { if (c->ipc_owner) cudaFree(c->ipc_frame); else cudaIpcCloseMemHandle(c->ipc_frame); c->ipc_frame = nullptr; }
+        c->ipc_state = -1;
+    } else { c->ipc_state = 1; c->ipc_frame_px = npx; c->ipc_parity = 0; }
+    return RTIOW_OK;
+}
+
+// tile + gathered buffers of the NCCL gather; allocated with ncclMemAlloc and registered as a symmetric window when the
+// library offers it (NCCL >= 2.27: zero-copy all-gather over NVLink), plain cudaMalloc otherwise.  Collective.
+static int ensure_nccl_buffers(rtiow_ctx* c, size_t tile_px, cudaStream_t st)
+{
+    DeviceState& d = c->dev[0];
+    if (c->nccl_tile_px == tile_px && c->nccl_tiles) return RTIOW_OK;
+    CU(cudaStreamSynchronize(st));
+    if (c->windows_registered && g_nccl.CommWindowDeregister) {
+        if (c->win_tiles) g_nccl.CommWindowDeregister(c->comm, (ncclWindow_t)c->win_tiles);
+        if (c->win_gathered) g_nccl.CommWindowDeregister(c->comm, (ncclWindow_t)c->win_gathered);
+    }
+    c->win_tiles = c->win_gathered = nullptr; c->windows_registered = false;
+    if (c->nccl_tiles && g_nccl.MemFree) { g_nccl.MemFree(c->nccl_tiles); g_nccl.MemFree(c->nccl_gathered); }
+    c->nccl_tiles = c->nccl_gathered = nullptr; c->nccl_tile_px = 0;
+    int ok = 0;
+    if (g_nccl.MemAlloc && g_nccl.MemFree && g_nccl.CommWindowRegister && g_nccl.CommWindowDeregister) {
+        ok = g_nccl.MemAlloc((void**)&c->nccl_tiles, tile_px * 4) == ncclSuccess && g_nccl.MemAlloc((void**)&c->nccl_gathered, tile_px * 4 * c->world) == ncclSuccess;
+        if (!ok) cudaGetLastError();
+    }
+    int all = 0;
+    int rc = nccl_vote_min(c, ok, &all, st); if (rc) return rc;
+    if (all) {
+        ncclWindow_t wt = nullptr, wg = nullptr;
+        const bool reg = g_nccl.CommWindowRegister(c->comm, c->nccl_tiles, tile_px * 4, &wt, NCCL_WIN_COLL_SYMMETRIC) == ncclSuccess &&
+                         g_nccl.CommWindowRegister(c->comm, c->nccl_gathered, tile_px * 4 * c->world, &wg, NCCL_WIN_COLL_SYMMETRIC) == ncclSuccess;
+        c->win_tiles = wt; c->win_gathered = wg; c->windows_registered = reg && wt && wg;
+        if (!reg) cudaGetLastError();
+    } else {
+        if (c->nccl_tiles) g_nccl.MemFree(c->nccl_tiles);
+        if (c->nccl_gathered) g_nccl.MemFree(c->nccl_gathered);
+        c->nccl_tiles = c->nccl_gathered = nullptr;
+        CU(d.tiles.resize(tile_px)); CU(d.gathered.resize(tile_px * c->world));
+    }
+    c->nccl_tile_px = tile_px;
+    return RTIOW_OK;
+}
+
+static int render_rank_impl(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_params* p, uint8_t* out_rgba, const void** d_frame_out, rtiow_stats* stats)
+{
+    if (!c || !cam) return fail(RTIOW_ERR_INVALID_ARG, "NULL argument");
+    int rc = check_params(p); if (rc) return rc;
+    if (c->dev.size() != 1) return fail(RTIOW_ERR_INVALID_ARG, "rtiow_render_rank needs a ctx from rtiow_ctx_create_rank (one device per process)");
+    if (c->rank == 0 && !out_rgba && !d_frame_out) return fail(RTIOW_ERR_INVALID_ARG, "rank 0 needs out_rgba (host) or d_frame (device)");
+    DeviceState& d = c->dev[0];
+    CU(cudaSetDevice(d.device));
+    cudaStream_t st = d.stream;
+    const double t0 = now_ms();
+    const uint32_t world = (uint32_t)c->world, rank = (uint32_t)c->rank;
+    const size_t npx = (size_t)p->width * p->height, frame_bytes = npx * 4;
+    const size_t tile_px = (size_t)max_rows_per_rank(p->height, p->tile_rows, world) * p->width;
+    uint32_t launches = 0;
+    const uint32_t* d_final = nullptr;
+    bool frame_here = true;                                 // d_final holds the whole frame on THIS rank
+    if (world == 1) {
+        CU(d.tiles.resize(tile_px));
+        CU(cudaEventRecord(d.ev0, st));
+        rc = render_tiles(c, d, cam, p, 0, 1, d.tiles.p, st, &launches); if (rc) return rc;
+        CU(cudaEventRecord(d.ev1, st));
+        d_final = d.tiles.p;
+        c->gather_note = "single GPU: no gather";
+    } else {
+        bool fused = false;
+        if (c->gather != RTIOW_GATHER_NCCL) {
+            rc = ensure_ipc_frame(c, npx, st); if (rc) return rc;
+            fused = c->ipc_state == 1;
+            if (c->gather == RTIOW_GATHER_FUSED && !fused)
+                return fail(RTIOW_ERR_UNSUPPORTED, "RTIOW_GATHER_FUSED: rank 0's frame could not be mapped into every rank (CUDA IPC / peer access)");
+        }
+        char note[256];
+        if (fused) {
+            // every rank's epilogue stores its rows straight into rank 0's frame (NVLink peer memory); the 1-int all-reduce after
+            // it is the frame-complete barrier.  Two frames alternate, so rank 0's copy-out of frame k is ordered (by its stream
+            // and the barrier of frame k+1) before anybody writes that buffer again in frame k+2.
+            uint32_t* fr = c->ipc_frame + (size_t)(c->ipc_parity & 1u) * npx; c->ipc_parity ^= 1u;
+            CU(cudaEventRecord(d.ev0, st));
+            rc = render_tiles(c, d, cam, p, rank, world, nullptr, st, &launches, fr); if (rc) return rc;
+            CU(cudaEventRecord(d.ev1, st));
+            rc = nccl_barrier(c, st); if (rc) return rc;
+            d_final = fr; frame_here = rank == 0;
+            snprintf(note, sizeof note, "one process per GPU x%u: epilogue stores into rank 0's frame over NVLink (CUDA IPC mapping made inside librtiow_cuda.so) + "
+                     "1-int ncclAllReduce as the frame-complete barrier (NCCL %d.%d.%d)", world, g_nccl.version / 10000, (g_nccl.version / 100) % 100, g_nccl.version % 100);
+        } else {
+            rc = ensure_nccl_buffers(c, tile_px, st); if (rc) return rc;
+            uint32_t* tiles = c->nccl_tiles ? c->nccl_tiles : d.tiles.p;
+            uint32_t* gathered = c->nccl_gathered ? c->nccl_gathered : d.gathered.p;
+            CU(d.frame.resize(npx));
+            CU(cudaEventRecord(d.ev0, st));
+            rc = render_tiles(c, d, cam, p, rank, world, tiles, st, &launches); if (rc) return rc;
+            CU(cudaEventRecord(d.ev1, st));
+            NC(g_nccl.AllGather(tiles, gathered, tile_px * 4, ncclUint8, c->comm, st));      // one per frame, equal (padded) counts: SURVEY §8(e)
+            deinterleave_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, st>>>(gathered, p->width, p->height, p->tile_rows, world, tile_px, d.frame.p);
+            CU(cudaGetLastError());
+            ++launches;
+            d_final = d.frame.p;
+            snprintf(note, sizeof note, "one process per GPU x%u: tile buffers + ncclAllGather inside librtiow_cuda.so (NCCL %d.%d.%d%s) + de-interleave", world,
+                     g_nccl.version / 10000, (g_nccl.version / 100) % 100, g_nccl.version % 100,
+                     c->windows_registered ? ", buffers from ncclMemAlloc registered as a symmetric window" : "");
+        }
+        c->gather_note = note;
+    }
+    if (out_rgba && frame_here) {
+        if (d.pinned_bytes < frame_bytes) {
+            if (d.pinned) cudaFreeHost(d.pinned);
+            d.pinned = nullptr; d.pinned_bytes = 0;
+            CU(cudaMallocHost(&d.pinned, frame_bytes)); d.pinned_bytes = frame_bytes;
+        }
+        CU(cudaMemcpyAsync(d.pinned, d_final, frame_bytes, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaMemcpyAsync(d.pinned_cnt, d.counters.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (out_rgba && frame_here) memcpy(out_rgba, d.pinned, frame_bytes);
+    if (d_frame_out) *d_frame_out = frame_here ? d_final : nullptr;
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        float ms = 0; CU(cudaEventElapsedTime(&ms, d.ev0, d.ev1));
+        stats->kernel_ms = ms; stats->total_ms = now_ms() - t0;
+        stats->paths = (uint64_t)rows_of_rank(p->height, p->tile_rows, world, rank) * p->width * p->spp;
+        stats->rays_traced = d.pinned_cnt[1]; stats->sphere_tests = stats->rays_traced * (uint64_t)d.scene.n;
+        stats->h2d_bytes = sizeof(rtiow_camera) + sizeof(rtiow_params); stats->d2h_bytes = (out_rgba && frame_here ? frame_bytes : 0) + 16;
+        stats->kernel_launches = launches; stats->n_gpus = world; stats->scan_backend = (uint32_t)d.last_backend;
+    }
+    return RTIOW_OK;
+}
+
+extern "C" int rtiow_render_rank(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_params* p, uint8_t* out_rgba, rtiow_stats* stats)
+{
+    return render_rank_impl(c, cam, p, out_rgba, nullptr, stats);
+}
+extern "C" int rtiow_render_rank_device(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_params* p, const void** d_frame, rtiow_stats* stats)
+{
+    if (!d_frame) return fail(RTIOW_ERR_INVALID_ARG, "d_frame is NULL");
+    return render_rank_impl(c, cam, p, nullptr, d_frame, stats);
 }
 
 // ------------------------------------------------------------------------------------------------
