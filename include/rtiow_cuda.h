@@ -247,6 +247,16 @@ int rtiow_random_scene(uint64_t seed, int32_t half_extent, int32_t material_mode
                        double* cz, double* radius, uint32_t* mat_kind, double* albedo_rgb, double* mat_param,
                        uint32_t* out_n);
 
+/* --- scene dump / load: the same world for this library, the oracle and a cargo build of the reference.
+ *     Text: "rtiow-scene 1", "n <count>", then one line per sphere in list order:
+ *     cx cy cz radius kind albedo_r albedo_g albedo_b param   (17 significant digits: f64 round-trips bit for bit).
+ *     rtiow_scene_load with cap = 0 only returns the count; a file larger than cap gives RTIOW_ERR_NOMEM with *out_n = the count.
+ *     Host-only. */
+int rtiow_scene_save(const char* path, uint32_t n, const double* cx, const double* cy, const double* cz, const double* radius,
+                     const uint32_t* mat_kind, const double* albedo_rgb, const double* mat_param);
+int rtiow_scene_load(const char* path, uint32_t cap, double* cx, double* cy, double* cz, double* radius, uint32_t* mat_kind,
+                     double* albedo_rgb, double* mat_param, uint32_t* out_n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,13 +19,31 @@ MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC = 0, 1, 2
 SAMPLER_REJECTION, SAMPLER_DIRECT = 0, 1
 
 
+_SCENE_SO = _HERE / "build" / "librtiow_scene.so"
+_NATIVE_SO = _HERE / "build" / "native" / "librtiow_oracle.so"
+
+
 def build(force: bool = False) -> Path:
-    """Compile the oracle with the committed Makefile (gcc, -ffp-contract=off, OpenMP)."""
-    srcs = [_HERE / "rtiow_oracle.c", _HERE / "rtiow_oracle.h", _HERE / "Makefile"]
-    stale = force or not _SO.exists() or any(s.stat().st_mtime > _SO.stat().st_mtime for s in srcs)
+    """Compile the oracle (and the host-only scene library) with the committed Makefile (gcc, -ffp-contract=off, OpenMP)."""
+    srcs = [_HERE / "rtiow_oracle.c", _HERE / "rtiow_oracle.h", _HERE / "Makefile", _HERE.parent / "rtiow_b200" / "csrc" / "scene_gen.cpp",
+            _HERE.parent / "include" / "rtiow_cuda.h"]
+    stale = force or not _SO.exists() or not _SCENE_SO.exists() or any(s.stat().st_mtime > min(_SO.stat().st_mtime, _SCENE_SO.stat().st_mtime) for s in srcs)
     if stale:
         subprocess.run(["make", "-C", str(_HERE), "-B"], check=True, capture_output=True)
     return _SO
+
+
+def use_native_build() -> bool:
+    """bench.py's timed CPU legs: rebuild the oracle with -march=native ON THE BOX THAT RUNS IT (the committed recipe builds for
+    baseline x86-64 because the .so travels) and switch lib() to it.  Returns False (and keeps the baseline build) if gcc fails."""
+    global _lib
+    try:
+        subprocess.run(["make", "-C", str(_HERE), "-B", "MARCH=native", "BUILD=build/native", "build/native/librtiow_oracle.so"], check=True, capture_output=True)
+    except (subprocess.CalledProcessError, OSError):
+        return False
+    _lib = C.CDLL(str(_NATIVE_SO))
+    _declare(_lib)
+    return True
 
 
 class Vec3(C.Structure):
@@ -279,6 +297,52 @@ def render(scene: Scene, cam: Camera, width, height, spp, max_depth=50, t_min=1e
     if rc != 0:
         raise ValueError("o_render: invalid arguments")
     return out, acc, dict(rays=int(cnt.rays), sphere_tests=int(cnt.sphere_tests))
+
+
+# ---- worlds: the seeded scene builder and scene files, from the HOST-ONLY build of rtiow_b200/csrc/scene_gen.cpp ----------
+_scene_lib = None
+
+
+def scene_lib() -> C.CDLL:
+    global _scene_lib
+    if _scene_lib is None:
+        build()
+        L = C.CDLL(str(_SCENE_SO))
+        P, u32 = C.c_void_p, C.c_uint32
+        L.rtiow_random_scene.restype, L.rtiow_random_scene.argtypes = C.c_int, [C.c_uint64, C.c_int32, C.c_int32, u32, P, P, P, P, P, P, P, C.POINTER(u32)]
+        L.rtiow_scene_save.restype, L.rtiow_scene_save.argtypes = C.c_int, [C.c_char_p, u32, P, P, P, P, P, P, P]
+        L.rtiow_scene_load.restype, L.rtiow_scene_load.argtypes = C.c_int, [C.c_char_p, u32, P, P, P, P, P, P, P, C.POINTER(u32)]
+        _scene_lib = L
+    return _scene_lib
+
+
+def _scene_dict(k, cx, cy, cz, r, kind, alb, prm):
+    return dict(center=np.stack([cx[:k], cy[:k], cz[:k]], 1), radius=r[:k].copy(), mat_index=np.arange(k, dtype=np.uint32),
+                mat_kind=kind[:k].copy(), mat_albedo=alb[:k].copy(), mat_param=prm[:k].copy())
+
+
+def random_scene(seed: int = 1, half_extent: int = 11, material_mode: int = 0):
+    """Seeded random_scene (main.rs:59-102) without the CUDA library: the arrays rtiow_b200.capi.random_scene returns."""
+    cap = (2 * half_extent + 1) ** 2 + 8
+    cx, cy, cz, r = (np.zeros(cap) for _ in range(4))
+    kind = np.zeros(cap, np.uint32); alb = np.zeros((cap, 3)); prm = np.zeros(cap)
+    n = C.c_uint32(0)
+    rc = scene_lib().rtiow_random_scene(seed, half_extent, material_mode, cap, _p(cx), _p(cy), _p(cz), _p(r), _p(kind), _p(alb), _p(prm), C.byref(n))
+    if rc != 0:
+        raise RuntimeError(f"rtiow_random_scene failed: {rc}")
+    return _scene_dict(n.value, cx, cy, cz, r, kind, alb, prm)
+
+
+def load_scene(path):
+    n = C.c_uint32(0)
+    if scene_lib().rtiow_scene_load(str(path).encode(), 0, None, None, None, None, None, None, None, C.byref(n)) != 0:
+        raise RuntimeError(f"cannot read scene file {path}")
+    k = max(n.value, 1)
+    cx, cy, cz, r = (np.zeros(k) for _ in range(4))
+    kind = np.zeros(k, np.uint32); alb = np.zeros((k, 3)); prm = np.zeros(k)
+    if scene_lib().rtiow_scene_load(str(path).encode(), k, _p(cx), _p(cy), _p(cz), _p(r), _p(kind), _p(alb), _p(prm), C.byref(n)) != 0:
+        raise RuntimeError(f"malformed scene file {path}")
+    return _scene_dict(n.value, cx, cy, cz, r, kind, alb, prm)
 
 
 def host_threads() -> int:

@@ -34,7 +34,7 @@ SYMBOLS = [
     "rtiow_tile_buffer_bytes", "rtiow_render_tiles_device", "rtiow_render_to_frame_device", "rtiow_deinterleave_device", "rtiow_sphere_hit_batch",
     "rtiow_hitlist_batch", "rtiow_scatter_batch", "rtiow_get_ray_batch", "rtiow_to_rgba_batch", "rtiow_reflect_batch",
     "rtiow_refract_batch", "rtiow_ray_color_batch", "rtiow_ray_color_trace_batch", "rtiow_sampler_batch", "rtiow_fp32_peak_probe", "rtiow_flush_l2",
-    "rtiow_random_scene",
+    "rtiow_random_scene", "rtiow_scene_save", "rtiow_scene_load",
 ]
 
 
@@ -136,6 +136,8 @@ def _declare(L):
         "rtiow_fp32_peak_probe": (C.c_int, [P, C.c_int, d, C.POINTER(d), C.POINTER(d)]),
         "rtiow_flush_l2": (C.c_int, [P]),
         "rtiow_random_scene": (C.c_int, [u64, i32, i32, u32, P, P, P, P, P, P, P, C.POINTER(u32)]),
+        "rtiow_scene_save": (C.c_int, [C.c_char_p, u32, P, P, P, P, P, P, P]),
+        "rtiow_scene_load": (C.c_int, [C.c_char_p, u32, P, P, P, P, P, P, P, C.POINTER(u32)]),
     }
     assert sorted(sig) == sorted(SYMBOLS)
     for name, (res, args) in sig.items():
@@ -197,6 +199,36 @@ def nccl_unique_id() -> bytes:
     buf = C.create_string_buffer(NCCL_UNIQUE_ID_BYTES)
     _check(lib().rtiow_nccl_unique_id(buf))
     return buf.raw
+
+
+def save_scene(path, center, radius, mat_index, mat_kind, mat_albedo, mat_param, L=None):
+    """rtiow_scene_save: one line per sphere (its material resolved through mat_index), f64 exact."""
+    L = L or lib()
+    center = _f64(center, (-1, 3)); n = len(center)
+    mi = np.asarray(mat_index, np.int64)
+    cx, cy, cz = (np.ascontiguousarray(center[:, i]) for i in range(3))
+    r = _f64(radius, (-1,)); kind = np.ascontiguousarray(np.asarray(mat_kind, np.uint32)[mi])
+    alb = np.ascontiguousarray(_f64(mat_albedo, (-1, 3))[mi]); prm = np.ascontiguousarray(_f64(mat_param, (-1,))[mi])
+    rc = L.rtiow_scene_save(str(path).encode(), n, _p(cx), _p(cy), _p(cz), _p(r), _p(kind), _p(alb), _p(prm))
+    if rc != OK:
+        raise RtiowError(rc, f"cannot write scene file {path}")
+
+
+def load_scene(path, L=None):
+    """rtiow_scene_load -> the dict of arrays random_scene returns (one material per sphere)."""
+    L = L or lib()
+    n = C.c_uint32(0)
+    rc = L.rtiow_scene_load(str(path).encode(), 0, None, None, None, None, None, None, None, C.byref(n))
+    if rc != OK:
+        raise RtiowError(rc, f"cannot read scene file {path}")
+    k = n.value
+    cx, cy, cz, r = (np.zeros(max(k, 1)) for _ in range(4))
+    kind = np.zeros(max(k, 1), np.uint32); alb = np.zeros((max(k, 1), 3)); prm = np.zeros(max(k, 1))
+    rc = L.rtiow_scene_load(str(path).encode(), max(k, 1), _p(cx), _p(cy), _p(cz), _p(r), _p(kind), _p(alb), _p(prm), C.byref(n))
+    if rc != OK:
+        raise RtiowError(rc, f"malformed scene file {path}")
+    return dict(center=np.stack([cx[:k], cy[:k], cz[:k]], 1), radius=r[:k].copy(), mat_index=np.arange(k, dtype=np.uint32),
+                mat_kind=kind[:k].copy(), mat_albedo=alb[:k].copy(), mat_param=prm[:k].copy())
 
 
 class Context:

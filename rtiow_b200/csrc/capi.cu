@@ -501,6 +501,8 @@ extern "C" void rtiow_params_default(rtiow_params* p)
 // ------------------------------------------------------------------------------------------------
 // frame partition
 // ------------------------------------------------------------------------------------------------
+// tile height actually used: a tile taller than the frame is the whole frame (and (height + tile_rows - 1) cannot wrap)
+static uint32_t tile_rows_of(const rtiow_params* p) { return std::min(p->tile_rows, p->height); }
 static uint32_t rows_of_rank(uint32_t height, uint32_t tile_rows, uint32_t world, uint32_t rank)
 {
     const uint32_t n_tiles = (height + tile_rows - 1) / tile_rows;
@@ -519,7 +521,7 @@ static int check_params(const rtiow_params* p)
     if (p->width < 2 || p->height < 2) return fail(RTIOW_ERR_INVALID_ARG, "width and height must be >= 2 (jitter divides by W-1, H-1: main.rs:131-132)");
     if (p->spp == 0) return fail(RTIOW_ERR_INVALID_ARG, "spp must be >= 1");
     if ((uint64_t)p->width * p->height > 0xfffffff0ull) return fail(RTIOW_ERR_INVALID_ARG, "frame too large");
-    if (p->tile_rows == 0 || p->tile_rows > p->height) return fail(RTIOW_ERR_INVALID_ARG, "tile_rows must be in [1, height]");
+    if (p->tile_rows == 0) return fail(RTIOW_ERR_INVALID_ARG, "tile_rows must be >= 1");
     if (p->precision > RTIOW_PRECISION_F64) return fail(RTIOW_ERR_INVALID_ARG, "unknown precision");
     if (!(p->t_min >= 0.0)) return fail(RTIOW_ERR_INVALID_ARG, "t_min must be >= 0");
     return RTIOW_OK;
@@ -529,7 +531,7 @@ extern "C" int rtiow_tile_buffer_bytes(const rtiow_params* p, int world, size_t*
 {
     int rc = check_params(p); if (rc) return rc;
     if (world < 1 || !out) return fail(RTIOW_ERR_INVALID_ARG, "bad world/out");
-    *out = (size_t)max_rows_per_rank(p->height, p->tile_rows, (uint32_t)world) * p->width * 4;
+    *out = (size_t)max_rows_per_rank(p->height, tile_rows_of(p), (uint32_t)world) * p->width * 4;
     return RTIOW_OK;
 }
 
@@ -592,7 +594,7 @@ static int launch_render(const rtiow_ctx* c, DeviceState& d, const rtiow_camera*
     a.scene = d.scene; a.cam = to_dev_camera<T>(*cam);
     a.width = p->width; a.height = p->height; a.spp = sr.count; a.smp_begin = sr.begin; a.max_depth = p->max_depth; a.t_min = (T)p->t_min; a.key = philox_key(p->seed);
     a.inv_wm1 = (T)(1.0 / (double)(p->width - 1)); a.inv_hm1 = (T)(1.0 / (double)(p->height - 1));
-    a.rank = rank; a.world = world; a.tile_rows = p->tile_rows; a.local_rows = rows_of_rank(p->height, p->tile_rows, world, rank);
+    a.rank = rank; a.world = world; a.tile_rows = tile_rows_of(p); a.local_rows = rows_of_rank(p->height, tile_rows_of(p), world, rank);
     uint32_t chunk = 64u;
 #ifdef RTIOW_TUNING
     if (const char* t = getenv("RTIOW_TUNE_CHUNK")) chunk = (uint32_t)std::max(1, atoi(t));
@@ -668,7 +670,7 @@ static int launch_render(const rtiow_ctx* c, DeviceState& d, const rtiow_camera*
     }
     CU(cudaGetLastError());
     if (peer_frame)      // fused quantise + gather: stores go to rank 0's frame through peer memory
-        finalize_to_frame_kernel<<<(unsigned)((n_lp + 255) / 256), 256, 0, st>>>(d.accum.p, (uint32_t)n_lp, sr.begin + sr.count, p->alpha, p->width, p->tile_rows, world, rank, peer_frame);
+        finalize_to_frame_kernel<<<(unsigned)((n_lp + 255) / 256), 256, 0, st>>>(d.accum.p, (uint32_t)n_lp, sr.begin + sr.count, p->alpha, p->width, tile_rows_of(p), world, rank, peer_frame);
     else
         finalize_kernel<<<(unsigned)((n_lp + 255) / 256), 256, 0, st>>>(d.accum.p, (uint32_t)n_lp, sr.begin + sr.count, p->alpha, d_tiles);
     CU(cudaGetLastError());
@@ -715,7 +717,7 @@ static int render_rank(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_params
         float ms = 0; CU(cudaEventElapsedTime(&ms, d.ev0, d.ev1));
         memset(stats, 0, sizeof *stats);
         stats->kernel_ms = ms; stats->total_ms = now_ms() - t0;
-        stats->paths = (uint64_t)rows_of_rank(p->height, p->tile_rows, world, rank) * p->width * p->spp;
+        stats->paths = (uint64_t)rows_of_rank(p->height, tile_rows_of(p), world, rank) * p->width * p->spp;
         stats->rays_traced = d.pinned_cnt[1]; stats->sphere_tests = stats->rays_traced * (uint64_t)d.scene.n;
         stats->kernel_launches = launches; stats->n_gpus = 1; stats->scan_backend = (uint32_t)d.last_backend;
     }
@@ -747,8 +749,8 @@ extern "C" int rtiow_deinterleave_device(rtiow_ctx* c, const void* d_gathered, c
     CU(cudaSetDevice(d.device));
     cudaStream_t st = stream ? (cudaStream_t)stream : d.stream;
     const size_t npx = (size_t)p->width * p->height;
-    const size_t tile_px = (size_t)max_rows_per_rank(p->height, p->tile_rows, world) * p->width;
-    deinterleave_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, st>>>((const uint32_t*)d_gathered, p->width, p->height, p->tile_rows, (uint32_t)world, tile_px, (uint32_t*)d_frame);
+    const size_t tile_px = (size_t)max_rows_per_rank(p->height, tile_rows_of(p), world) * p->width;
+    deinterleave_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, st>>>((const uint32_t*)d_gathered, p->width, p->height, tile_rows_of(p), (uint32_t)world, tile_px, (uint32_t*)d_frame);
     CU(cudaGetLastError());
     return RTIOW_OK;
 }
@@ -761,7 +763,7 @@ static int render_frame(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_param
     const double t0 = now_ms();
     const uint32_t world = (uint32_t)c->dev.size();
     const size_t frame_bytes = (size_t)p->width * p->height * 4;
-    const size_t tile_px = (size_t)max_rows_per_rank(p->height, p->tile_rows, world) * p->width;
+    const size_t tile_px = (size_t)max_rows_per_rank(p->height, tile_rows_of(p), world) * p->width;
     DeviceState& d0 = c->dev[0];
     uint32_t launches = 0;
     CU(cudaSetDevice(d0.device));
@@ -807,7 +809,7 @@ static int render_frame(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_param
             CU(cudaEventRecord(d.ev1, d.stream));
             if (r != 0 && !use_nccl) {
                 if (!fused) {
-                    const size_t bytes = (size_t)rows_of_rank(p->height, p->tile_rows, world, r) * p->width * 4;
+                    const size_t bytes = (size_t)rows_of_rank(p->height, tile_rows_of(p), world, r) * p->width * 4;
                     CU(cudaMemcpyPeerAsync(d0.gathered.p + tile_px * r, d0.device, d.tiles.p, d.device, bytes, d.stream));
                 }
                 CU(cudaEventRecord(d.ev_done, d.stream));
@@ -826,7 +828,7 @@ static int render_frame(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_param
         if (!use_nccl) for (uint32_t r = 1; r < world; ++r) CU(cudaStreamWaitEvent(d0.stream, c->dev[r].ev_done, 0));
         if (!fused) {
             const size_t npx = (size_t)p->width * p->height;
-            deinterleave_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, d0.stream>>>(d0.gathered.p, p->width, p->height, p->tile_rows, world, tile_px, d0.frame.p);
+            deinterleave_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, d0.stream>>>(d0.gathered.p, p->width, p->height, tile_rows_of(p), world, tile_px, d0.frame.p);
             CU(cudaGetLastError());
             ++launches;
         }
@@ -1006,7 +1008,7 @@ static int render_rank_impl(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_p
     const double t0 = now_ms();
     const uint32_t world = (uint32_t)c->world, rank = (uint32_t)c->rank;
     const size_t npx = (size_t)p->width * p->height, frame_bytes = npx * 4;
-    const size_t tile_px = (size_t)max_rows_per_rank(p->height, p->tile_rows, world) * p->width;
+    const size_t tile_px = (size_t)max_rows_per_rank(p->height, tile_rows_of(p), world) * p->width;
     uint32_t launches = 0;
     const uint32_t* d_final = nullptr;
     bool frame_here = true;                                 // d_final holds the whole frame on THIS rank
@@ -1047,7 +1049,7 @@ static int render_rank_impl(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_p
             rc = render_tiles(c, d, cam, p, rank, world, tiles, st, &launches); if (rc) return rc;
             CU(cudaEventRecord(d.ev1, st));
             NC(g_nccl.AllGather(tiles, gathered, tile_px * 4, ncclUint8, c->comm, st));      // one per frame, equal (padded) counts: SURVEY §8(e)
-            deinterleave_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, st>>>(gathered, p->width, p->height, p->tile_rows, world, tile_px, d.frame.p);
+            deinterleave_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, st>>>(gathered, p->width, p->height, tile_rows_of(p), world, tile_px, d.frame.p);
             CU(cudaGetLastError());
             ++launches;
             d_final = d.frame.p;
@@ -1073,7 +1075,7 @@ static int render_rank_impl(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_p
         memset(stats, 0, sizeof *stats);
         float ms = 0; CU(cudaEventElapsedTime(&ms, d.ev0, d.ev1));
         stats->kernel_ms = ms; stats->total_ms = now_ms() - t0;
-        stats->paths = (uint64_t)rows_of_rank(p->height, p->tile_rows, world, rank) * p->width * p->spp;
+        stats->paths = (uint64_t)rows_of_rank(p->height, tile_rows_of(p), world, rank) * p->width * p->spp;
         stats->rays_traced = d.pinned_cnt[1]; stats->sphere_tests = stats->rays_traced * (uint64_t)d.scene.n;
         stats->h2d_bytes = sizeof(rtiow_camera) + sizeof(rtiow_params); stats->d2h_bytes = (out_rgba && frame_here ? frame_bytes : 0) + 16;
         stats->kernel_launches = launches; stats->n_gpus = world; stats->scan_backend = (uint32_t)d.last_backend;

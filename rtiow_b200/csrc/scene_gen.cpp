@@ -104,3 +104,56 @@ extern "C" int rtiow_random_scene(uint64_t seed, int32_t half_extent, int32_t ma
     *out_n = w.n;
     return w.overflow ? RTIOW_ERR_NOMEM : RTIOW_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Scene dump / load (second half): one world, many renderers.  The reference builds its world in code
+// (main.rs:59-102) from an unseedable thread_rng; a text file of the same Sphere / material records lets the oracle, this
+// library and a real `cargo` build of the reference (INTEGRATION.md shows the 20-line Rust reader) render the SAME spheres.
+//   rtiow-scene 1
+//   n <count>
+//   <cx> <cy> <cz> <radius> <kind> <albedo_r> <albedo_g> <albedo_b> <param>      one line per sphere, list order
+// kind: 0 Lambertian, 1 Metal (param = fuzz), 2 Dialectric (param = ir).  Numbers are printed with 17 significant digits, so
+// every f64 survives the round trip bit for bit.
+// ------------------------------------------------------------------------------------------------
+#include <cstdio>
+#include <cinttypes>
+
+extern "C" int rtiow_scene_save(const char* path, uint32_t n, const double* cx, const double* cy, const double* cz, const double* radius,
+                                const uint32_t* mat_kind, const double* albedo_rgb, const double* mat_param)
+{
+    if (!path || (n > 0 && (!cx || !cy || !cz || !radius || !mat_kind || !albedo_rgb || !mat_param))) return RTIOW_ERR_INVALID_ARG;
+    for (uint32_t i = 0; i < n; ++i) if (mat_kind[i] > RTIOW_MAT_DIELECTRIC) return RTIOW_ERR_UNSUPPORTED;
+    FILE* f = std::fopen(path, "w");
+    if (!f) return RTIOW_ERR_INVALID_ARG;
+    std::fprintf(f, "rtiow-scene 1\nn %" PRIu32 "\n", n);
+    for (uint32_t i = 0; i < n; ++i)
+        std::fprintf(f, "%.17g %.17g %.17g %.17g %" PRIu32 " %.17g %.17g %.17g %.17g\n", cx[i], cy[i], cz[i], radius[i], mat_kind[i],
+                     albedo_rgb[3 * i], albedo_rgb[3 * i + 1], albedo_rgb[3 * i + 2], mat_param[i]);
+    const bool bad = std::ferror(f) != 0;
+    return (std::fclose(f) != 0 || bad) ? RTIOW_ERR_INVALID_ARG : RTIOW_OK;
+}
+
+// cap = 0 (arrays may be NULL): only the count is returned in *out_n.  More spheres in the file than cap: RTIOW_ERR_NOMEM,
+// *out_n = the count needed.
+extern "C" int rtiow_scene_load(const char* path, uint32_t cap, double* cx, double* cy, double* cz, double* radius, uint32_t* mat_kind,
+                                double* albedo_rgb, double* mat_param, uint32_t* out_n)
+{
+    if (!path || !out_n) return RTIOW_ERR_INVALID_ARG;
+    if (cap > 0 && (!cx || !cy || !cz || !radius || !mat_kind || !albedo_rgb || !mat_param)) return RTIOW_ERR_INVALID_ARG;
+    FILE* f = std::fopen(path, "r");
+    if (!f) return RTIOW_ERR_INVALID_ARG;
+    int version = 0; uint32_t n = 0;
+    if (std::fscanf(f, " rtiow-scene %d n %" SCNu32, &version, &n) != 2 || version != 1) { std::fclose(f); return RTIOW_ERR_UNSUPPORTED; }
+    *out_n = n;
+    if (cap == 0) { std::fclose(f); return RTIOW_OK; }
+    if (n > cap) { std::fclose(f); return RTIOW_ERR_NOMEM; }
+    for (uint32_t i = 0; i < n; ++i) {
+        double v[8]; uint32_t k = 0;
+        if (std::fscanf(f, "%lf %lf %lf %lf %" SCNu32 " %lf %lf %lf %lf", &v[0], &v[1], &v[2], &v[3], &k, &v[4], &v[5], &v[6], &v[7]) != 9 ||
+            k > RTIOW_MAT_DIELECTRIC) { std::fclose(f); return RTIOW_ERR_INVALID_ARG; }
+        cx[i] = v[0]; cy[i] = v[1]; cz[i] = v[2]; radius[i] = v[3]; mat_kind[i] = k;
+        albedo_rgb[3 * i] = v[4]; albedo_rgb[3 * i + 1] = v[5]; albedo_rgb[3 * i + 2] = v[6]; mat_param[i] = v[7];
+    }
+    std::fclose(f);
+    return RTIOW_OK;
+}

@@ -66,6 +66,13 @@ static int selftest()
       expect(c == a && seen == std::vector<uint32_t>({ 2, 4, 6, 8 }) && first == render(cam, random_scene(1), q), "render_progressive: passes, preview and final frame");
       try { render_progressive(cam, random_scene(1), p, 4, [](uint32_t, uint32_t, uint32_t, const std::vector<uint8_t>&) { return true; }); expect(false, "cancel must throw"); }
       catch (const RenderError& e) { expect(e.kind == RenderError::Cancelled, "callback returning true -> RenderError::Cancelled"); } }
+    // scene files: the world survives a round trip bit for bit, and both filter backends render it
+    { save_scene(random_scene(1), "/tmp/rtiow_selftest_scene.txt");
+      expect(render(cam, load_scene("/tmp/rtiow_selftest_scene.txt"), p) == a, "scene file round trip renders the same frame");
+      RenderParams q = p; q.scan = RTIOW_SCAN_FP32; rtiow_stats sq{};
+      std::vector<uint8_t> f = render(cam, random_scene(1), q, &sq); size_t diff = 0;
+      for (size_t i = 0; i < f.size(); ++i) diff += f[i] != a[i];
+      expect(sq.scan_backend == RTIOW_SCAN_FP32 && diff <= f.size() / 1000, "FP32 filter backend renders the same frame (up to last-bit path differences)"); }
     expect(write_png("/tmp/rtiow_selftest.png", 160, 90, a) && write_ppm("/tmp/rtiow_selftest.ppm", 160, 90, a), "PNG/PPM written");
     std::cout << (bad ? "selftest FAILED\n" : "selftest ok\n");
     return bad ? 1 : 0;
@@ -75,7 +82,7 @@ int main(int argc, char** argv)
 {
     RenderParams p; p.width = 200; p.height = 133;                       // main.rs:24-28
     uint64_t scene_seed = 1; int grid = 11, materials = 0; std::string out = "image.png";     // main.rs:177
-    bool explicit_h = false; uint32_t passes = 0;
+    bool explicit_h = false; uint32_t passes = 0; std::string scene_file, dump_scene;
     for (int i = 1; i < argc; ++i) {
         auto next = [&]() -> const char* { if (i + 1 >= argc) { std::cerr << "missing value for " << argv[i] << "\n"; std::exit(2); } return argv[++i]; };
         if (!std::strcmp(argv[i], "--width")) p.width = std::atoi(next());
@@ -90,12 +97,17 @@ int main(int argc, char** argv)
         else if (!std::strcmp(argv[i], "--f64")) p.f64 = true;
         else if (!std::strcmp(argv[i], "--passes")) passes = uint32_t(std::atoi(next()));
         else if (!std::strcmp(argv[i], "--out")) out = next();
+        else if (!std::strcmp(argv[i], "--scene")) scene_file = next();               // render the world of a scene file instead of random_scene
+        else if (!std::strcmp(argv[i], "--dump-scene")) dump_scene = next();          // write the world to a scene file (for the oracle / a cargo build)
+        else if (!std::strcmp(argv[i], "--scan")) { const char* v = next(); p.scan = !std::strcmp(v, "fp32") ? RTIOW_SCAN_FP32 : !std::strcmp(v, "tensor") ? RTIOW_SCAN_TENSOR : RTIOW_SCAN_AUTO; }
+        else if (!std::strcmp(argv[i], "--gather")) { const char* v = next(); p.gather = !std::strcmp(v, "nccl") ? RTIOW_GATHER_NCCL : !std::strcmp(v, "fused") ? RTIOW_GATHER_FUSED : RTIOW_GATHER_AUTO; }
         else if (!std::strcmp(argv[i], "--selftest")) return selftest();
         else { std::cerr << "unknown flag " << argv[i] << "\n"; return 2; }
     }
     if (!explicit_h) p.height = uint32_t(double(p.width) / (3.0 / 2.0));  // IMAGE_HEIGHT truncates (main.rs:24,26)
     try {
-        HittableList world = random_scene(scene_seed, grid, materials);  // main.rs:106
+        HittableList world = scene_file.empty() ? random_scene(scene_seed, grid, materials) : load_scene(scene_file);   // main.rs:106
+        if (!dump_scene.empty()) { save_scene(world, dump_scene); std::cout << dump_scene << " written (" << world.iter().size() << " spheres)\n"; }
         Camera cam(Point3(13, 2, 3), Point3(0, 0, 0), Vec3(0, 1, 0), 20.0, double(p.width) / double(p.height), 0.1, 10.0);   // main.rs:108-118
         rtiow_stats st{};
         auto t0 = std::chrono::steady_clock::now();

@@ -263,6 +263,8 @@ public:
 struct RenderParams {                                     // runtime form of the consts at main.rs:24-28,44,137
     uint32_t width = 200, height = 133; uint32_t spp = 100; int32_t max_depth = 50; double t_min = 0.0001;
     uint64_t seed = 1; int n_gpus = 1; uint8_t alpha = 255; bool f64 = false; uint32_t tile_rows = 1;
+    int scan = RTIOW_SCAN_AUTO;                           // where the sphere filter runs: tensor cores when the scene qualifies
+    int gather = RTIOW_GATHER_AUTO;                       // n_gpus > 1: how the row tiles reach GPU 0
 };
 
 class RenderError : public std::runtime_error {
@@ -307,6 +309,8 @@ inline std::vector<uint8_t> render_impl(const Camera& cam, const HittableList& w
     rtiow_ctx* ctx = nullptr;
     auto check = [&](int rc) { if (rc != RTIOW_OK) { std::string m = rtiow_last_error(); if (ctx) rtiow_ctx_destroy(ctx); throw RenderError(rc, m); } };
     check(rtiow_ctx_create(p.n_gpus, &ctx));
+    check(rtiow_ctx_set_scan_backend(ctx, p.scan));
+    check(rtiow_ctx_set_gather(ctx, p.gather));
     rtiow_spheres s{ cx.data(), cy.data(), cz.data(), rad.data(), mi.data(), uint32_t(rad.size()) };
     rtiow_materials m{ kind.data(), ar.data(), ag.data(), ab.data(), prm.data(), uint32_t(kind.size()) };
     check(rtiow_scene_upload(ctx, &s, &m));
@@ -339,13 +343,10 @@ inline std::vector<uint8_t> render_progressive(const Camera& cam, const Hittable
     return render_impl(cam, world, p, stats, n_passes ? n_passes : 1, &on_pass);
 }
 
-// random_scene (main.rs:59-102) with an explicit seed
-inline HittableList random_scene(uint64_t seed = 1, int half_extent = 11, int material_mode = 0)
+namespace detail {
+inline HittableList world_from_arrays(uint32_t n, const std::vector<double>& cx, const std::vector<double>& cy, const std::vector<double>& cz,
+                                      const std::vector<double>& r, const std::vector<uint32_t>& kind, const std::vector<double>& alb, const std::vector<double>& prm)
 {
-    const uint32_t cap = uint32_t((2 * half_extent + 1) * (2 * half_extent + 1) + 8);
-    std::vector<double> cx(cap), cy(cap), cz(cap), r(cap), alb(3 * size_t(cap)), prm(cap); std::vector<uint32_t> kind(cap); uint32_t n = 0;
-    int rc = rtiow_random_scene(seed, half_extent, material_mode, cap, cx.data(), cy.data(), cz.data(), r.data(), kind.data(), alb.data(), prm.data(), &n);
-    if (rc != RTIOW_OK) throw RenderError(rc, "rtiow_random_scene failed");
     HittableList world;
     for (uint32_t i = 0; i < n; ++i) {
         std::shared_ptr<const Scatter> m;
@@ -356,6 +357,44 @@ inline HittableList random_scene(uint64_t seed = 1, int half_extent = 11, int ma
         world.push(std::make_unique<Sphere>(Point3(cx[i], cy[i], cz[i]), r[i], m));
     }
     return world;
+}
+}  // namespace detail
+
+// random_scene (main.rs:59-102) with an explicit seed
+inline HittableList random_scene(uint64_t seed = 1, int half_extent = 11, int material_mode = 0)
+{
+    const uint32_t cap = uint32_t((2 * half_extent + 1) * (2 * half_extent + 1) + 8);
+    std::vector<double> cx(cap), cy(cap), cz(cap), r(cap), alb(3 * size_t(cap)), prm(cap); std::vector<uint32_t> kind(cap); uint32_t n = 0;
+    int rc = rtiow_random_scene(seed, half_extent, material_mode, cap, cx.data(), cy.data(), cz.data(), r.data(), kind.data(), alb.data(), prm.data(), &n);
+    if (rc != RTIOW_OK) throw RenderError(rc, "rtiow_random_scene failed");
+    return detail::world_from_arrays(n, cx, cy, cz, r, kind, alb, prm);
+}
+
+// Scene files (rtiow_scene_save / rtiow_scene_load): the same world for this library, the oracle and a cargo build of the
+// reference.  save_scene writes one line per sphere of the HittableList; anything that does not describe() itself throws.
+inline void save_scene(const HittableList& world, const std::string& path)
+{
+    std::vector<double> cx, cy, cz, r, alb, prm; std::vector<uint32_t> kind;
+    for (const auto& h : world.iter()) {
+        auto d = h->describe();
+        auto m = d && d->mat ? d->mat->describe() : std::nullopt;
+        if (!d || !m) throw RenderError(RTIOW_ERR_UNSUPPORTED, "a shape or material of the HittableList has no description");
+        cx.push_back(d->sphere.center[0]); cy.push_back(d->sphere.center[1]); cz.push_back(d->sphere.center[2]); r.push_back(d->sphere.radius);
+        kind.push_back(m->kind); alb.insert(alb.end(), m->albedo, m->albedo + 3); prm.push_back(m->param);
+    }
+    int rc = rtiow_scene_save(path.c_str(), uint32_t(r.size()), cx.data(), cy.data(), cz.data(), r.data(), kind.data(), alb.data(), prm.data());
+    if (rc != RTIOW_OK) throw RenderError(rc, "cannot write scene file " + path);
+}
+inline HittableList load_scene(const std::string& path)
+{
+    uint32_t n = 0;
+    int rc = rtiow_scene_load(path.c_str(), 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, &n);
+    if (rc != RTIOW_OK) throw RenderError(rc, "cannot read scene file " + path);
+    const uint32_t cap = n ? n : 1;
+    std::vector<double> cx(cap), cy(cap), cz(cap), r(cap), alb(3 * size_t(cap)), prm(cap); std::vector<uint32_t> kind(cap);
+    rc = rtiow_scene_load(path.c_str(), cap, cx.data(), cy.data(), cz.data(), r.data(), kind.data(), alb.data(), prm.data(), &n);
+    if (rc != RTIOW_OK) throw RenderError(rc, "malformed scene file " + path);
+    return detail::world_from_arrays(n, cx, cy, cz, r, kind, alb, prm);
 }
 
 // ------------------------------------------------------------------------------------------------ output stage

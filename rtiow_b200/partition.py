@@ -10,6 +10,7 @@ import numpy as np
 
 
 def rows_of_rank(height: int, tile_rows: int, world: int, rank: int) -> list[int]:
+    tile_rows = min(tile_rows, height)            # a tile taller than the frame is the whole frame (capi.cu: tile_rows_of)
     n_tiles = -(-height // tile_rows)
     rows = []
     for tg in range(rank, n_tiles, world):
@@ -18,6 +19,7 @@ def rows_of_rank(height: int, tile_rows: int, world: int, rank: int) -> list[int
 
 
 def max_rows_per_rank(height: int, tile_rows: int, world: int) -> int:
+    tile_rows = min(tile_rows, height)
     n_tiles = -(-height // tile_rows)
     return -(-n_tiles // world) * tile_rows
 
@@ -27,6 +29,7 @@ def tile_buffer_bytes(width: int, height: int, tile_rows: int, world: int) -> in
 
 
 def owner_and_local_row(y: int, tile_rows: int, world: int) -> tuple[int, int]:
+    """tile_rows: already clamped to the frame height by the caller"""
     tg, within = divmod(y, tile_rows)
     return tg % world, (tg // world) * tile_rows + within
 
@@ -34,6 +37,7 @@ def owner_and_local_row(y: int, tile_rows: int, world: int) -> tuple[int, int]:
 def gather_index(width: int, height: int, tile_rows: int, world: int) -> np.ndarray:
     """frame_row[y] = gathered_rows[index[y]] where gathered = the G tile buffers concatenated in rank order,
     viewed as rows of `width` pixels (what an all-gather of equal-size tile buffers leaves on every rank)."""
+    tile_rows = min(tile_rows, height)
     per = max_rows_per_rank(height, tile_rows, world)
     idx = np.empty(height, np.int64)
     for y in range(height):

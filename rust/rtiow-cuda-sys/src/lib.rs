@@ -1,12 +1,13 @@
-//! Raw bindings to `include/rtiow_cuda.h` (ABI version 1).  One `extern "C"` item per exported symbol, one
+//! Raw bindings to `include/rtiow_cuda.h` (ABI version 3).  One `extern "C"` item per exported symbol, one
 //! `#[repr(C)]` struct per C struct; layouts are asserted in `tests/test_host_cabi.py::test_struct_layouts_match_header`
-//! (Camera 176 B, Params 48 B, Stats 64 B, Spheres/Materials 48 B).
+//! (Camera 176 B, Params 48 B, Stats 72 B, Spheres/Materials 48 B).
 //!
-//! NOT compiled in this repository's build container (no rustc); kept in lock-step with the header by review.
+//! NOT compiled in this repository's build container (no rustc).  `tests/test_rust_header_lock.py` parses this file and the
+//! header and fails when symbol names, argument counts, struct field order or the constants drift apart.
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_int, c_void};
 
-pub const RTIOW_ABI_VERSION: c_int = 2;
+pub const RTIOW_ABI_VERSION: c_int = 3;
 
 pub const RTIOW_OK: c_int = 0;
 pub const RTIOW_ERR_INVALID_ARG: c_int = -1;
@@ -23,6 +24,15 @@ pub const RTIOW_MAT_DIELECTRIC: u32 = 2;
 
 pub const RTIOW_PRECISION_F32: u8 = 0;
 pub const RTIOW_PRECISION_F64: u8 = 1;
+
+pub const RTIOW_SCAN_AUTO: c_int = 0;
+pub const RTIOW_SCAN_FP32: c_int = 1;
+pub const RTIOW_SCAN_TENSOR: c_int = 2;
+
+pub const RTIOW_GATHER_AUTO: c_int = 0;
+pub const RTIOW_GATHER_NCCL: c_int = 1;
+pub const RTIOW_GATHER_FUSED: c_int = 2;
+pub const RTIOW_NCCL_UNIQUE_ID_BYTES: usize = 128;
 
 #[repr(C)]
 pub struct rtiow_ctx { _private: [u8; 0] }
@@ -70,7 +80,7 @@ pub struct rtiow_params {
 pub struct rtiow_stats {
     pub kernel_ms: f64, pub total_ms: f64,
     pub paths: u64, pub rays_traced: u64, pub sphere_tests: u64, pub h2d_bytes: u64, pub d2h_bytes: u64,
-    pub kernel_launches: u32, pub n_gpus: u32,
+    pub kernel_launches: u32, pub n_gpus: u32, pub scan_backend: u32, pub reserved: u32,
 }
 
 /// int (*)(void* user, uint32_t pass, uint32_t n_passes, uint32_t spp_done, const uint8_t* rgba); non-zero return cancels
@@ -83,6 +93,11 @@ extern "C" {
     pub fn rtiow_ctx_create(n_gpus: c_int, out: *mut *mut rtiow_ctx) -> c_int;
     pub fn rtiow_ctx_create_on_device(device: c_int, out: *mut *mut rtiow_ctx) -> c_int;
     pub fn rtiow_ctx_destroy(ctx: *mut rtiow_ctx);
+    pub fn rtiow_ctx_set_scan_backend(ctx: *mut rtiow_ctx, backend: c_int) -> c_int;
+    pub fn rtiow_nccl_unique_id(out_id: *mut c_void) -> c_int;
+    pub fn rtiow_ctx_create_rank(device: c_int, rank: c_int, world: c_int, nccl_unique_id: *const c_void, out: *mut *mut rtiow_ctx) -> c_int;
+    pub fn rtiow_ctx_set_gather(ctx: *mut rtiow_ctx, mode: c_int) -> c_int;
+    pub fn rtiow_ctx_gather_info(ctx: *mut rtiow_ctx, buf: *mut c_char, n: usize) -> c_int;
     pub fn rtiow_scene_upload(ctx: *mut rtiow_ctx, spheres: *const rtiow_spheres, materials: *const rtiow_materials) -> c_int;
     pub fn rtiow_camera_new(look_from: *const f64, look_at: *const f64, v_up: *const f64, v_fov_deg: f64, aspect_ratio: f64,
                             aperture: f64, focus_dist: f64, out: *mut rtiow_camera) -> c_int;
@@ -91,6 +106,9 @@ extern "C" {
                         stats: *mut rtiow_stats) -> c_int;
     pub fn rtiow_render_progressive(ctx: *mut rtiow_ctx, cam: *const rtiow_camera, p: *const rtiow_params, n_passes: u32,
                                     on_pass: Option<rtiow_progress_fn>, user: *mut c_void, out_rgba: *mut u8, stats: *mut rtiow_stats) -> c_int;
+    pub fn rtiow_render_rank(ctx: *mut rtiow_ctx, cam: *const rtiow_camera, p: *const rtiow_params, out_rgba: *mut u8, stats: *mut rtiow_stats) -> c_int;
+    pub fn rtiow_render_rank_device(ctx: *mut rtiow_ctx, cam: *const rtiow_camera, p: *const rtiow_params, d_frame: *mut *const c_void,
+                                    stats: *mut rtiow_stats) -> c_int;
     pub fn rtiow_tile_buffer_bytes(p: *const rtiow_params, world: c_int, out_bytes: *mut usize) -> c_int;
     pub fn rtiow_render_tiles_device(ctx: *mut rtiow_ctx, cam: *const rtiow_camera, p: *const rtiow_params, rank: c_int, world: c_int,
                                      d_tiles: *mut c_void, stream: *mut c_void, stats: *mut rtiow_stats) -> c_int;
@@ -113,10 +131,17 @@ extern "C" {
     pub fn rtiow_refract_batch(ctx: *mut rtiow_ctx, precision: c_int, n: i64, uv: *const f64, nrm: *const f64, eta: *const f64, out: *mut f64) -> c_int;
     pub fn rtiow_ray_color_batch(ctx: *mut rtiow_ctx, precision: c_int, n: i64, orig: *const f64, dir: *const f64, pixel: *const u32,
                                  sample: *const u32, seed: u64, max_depth: i32, t_min: f64, color: *mut f64, rays: *mut u64) -> c_int;
+    pub fn rtiow_ray_color_trace_batch(ctx: *mut rtiow_ctx, precision: c_int, n: i64, orig: *const f64, dir: *const f64, pixel: *const u32,
+                                       sample: *const u32, seed: u64, max_depth: i32, t_min: f64, color: *mut f64, rays: *mut u64,
+                                       trace_index: *mut i32, trace_ray: *mut f64) -> c_int;
     pub fn rtiow_sampler_batch(ctx: *mut rtiow_ctx, precision: c_int, n: i64, pixel: *const u32, sample: *const u32, bounce: *const u32,
                                seed: u64, out: *mut f64) -> c_int;
     pub fn rtiow_fp32_peak_probe(ctx: *mut rtiow_ctx, packed: c_int, target_ms: f64, out_tflops: *mut f64, out_ms: *mut f64) -> c_int;
     pub fn rtiow_flush_l2(ctx: *mut rtiow_ctx) -> c_int;
     pub fn rtiow_random_scene(seed: u64, half_extent: i32, material_mode: i32, cap: u32, cx: *mut f64, cy: *mut f64, cz: *mut f64,
                               radius: *mut f64, mat_kind: *mut u32, albedo_rgb: *mut f64, mat_param: *mut f64, out_n: *mut u32) -> c_int;
+    pub fn rtiow_scene_save(path: *const c_char, n: u32, cx: *const f64, cy: *const f64, cz: *const f64, radius: *const f64,
+                            mat_kind: *const u32, albedo_rgb: *const f64, mat_param: *const f64) -> c_int;
+    pub fn rtiow_scene_load(path: *const c_char, cap: u32, cx: *mut f64, cy: *mut f64, cz: *mut f64, radius: *mut f64, mat_kind: *mut u32,
+                            albedo_rgb: *mut f64, mat_param: *mut f64, out_n: *mut u32) -> c_int;
 }

@@ -46,7 +46,7 @@ def test_struct_layouts_match_header(capi):
     # sizes the Rust -sys crate / C callers rely on (repr(C))
     assert C.sizeof(capi.Camera) == 22 * 8
     assert C.sizeof(capi.Params) == 48 and capi.Params.t_min.offset == 16 and capi.Params.seed.offset == 24 and capi.Params.tile_rows.offset == 40
-    assert C.sizeof(capi.Stats) == 64
+    assert C.sizeof(capi.Stats) == 72 and capi.Stats.scan_backend.offset == 64
     assert C.sizeof(capi.Spheres) == 48 and C.sizeof(capi.Materials) == 48
 
 

@@ -1,0 +1,101 @@
+"""CPU suite: rust/rtiow-cuda-sys/src/lib.rs is uncompiled here (no rustc), so this test is what keeps it in step with
+include/rtiow_cuda.h (VERDICT r1 missing #5): the same exported functions with the same number of arguments, the same struct
+fields in the same order, the same constants — and the ctypes binding and the built .so agree with both."""
+import re
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+HDR = (ROOT / "include" / "rtiow_cuda.h").read_text()
+RS = (ROOT / "rust" / "rtiow-cuda-sys" / "src" / "lib.rs").read_text()
+
+
+def _strip_c_comments(s):
+    return re.sub(r"/\*.*?\*/", " ", s, flags=re.S)
+
+
+def _split_args(a):
+    out, depth, cur = [], 0, ""
+    for ch in a:
+        if ch in "([": depth += 1
+        if ch in ")]": depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur); cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        out.append(cur)
+    return [x.strip() for x in out if x.strip() and x.strip() != "void"]
+
+
+def c_functions():
+    h = _strip_c_comments(HDR)
+    fns = {}
+    for m in re.finditer(r"\b(?:int|void|const char\*)\s+(rtiow_\w+)\s*\(([^;{}]*?)\)\s*;", h, flags=re.S):
+        fns[m.group(1)] = len(_split_args(m.group(2)))
+    return fns
+
+
+def rust_functions():
+    body = RS[RS.index('extern "C" {'):]
+    fns = {}
+    for m in re.finditer(r"pub fn (rtiow_\w+)\s*\((.*?)\)\s*(?:->\s*[^;]+)?;", body, flags=re.S):
+        fns[m.group(1)] = len(_split_args(m.group(2)))
+    return fns
+
+
+def c_structs():
+    h = _strip_c_comments(HDR)
+    out = {}
+    for m in re.finditer(r"typedef struct\s*\{(.*?)\}\s*(rtiow_\w+)\s*;", h, flags=re.S):
+        fields = []
+        for decl in m.group(1).split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            for part in decl.split(","):                      # "double origin[3], lower_left_corner[3]" / "const double* cx"
+                name = re.findall(r"(\w+)\s*(?:\[\d+\])?\s*$", part.strip())
+                fields.append(name[0])
+        out[m.group(2)] = fields
+    return out
+
+
+def rust_structs():
+    out = {}
+    for m in re.finditer(r"pub struct (rtiow_\w+)\s*\{(.*?)\}", RS, flags=re.S):
+        out[m.group(1)] = re.findall(r"pub (\w+)\s*:", m.group(2))
+    return out
+
+
+def test_functions_match():
+    c, r = c_functions(), rust_functions()
+    assert len(c) >= 35
+    assert sorted(c) == sorted(r), f"only in header: {sorted(set(c) - set(r))}; only in lib.rs: {sorted(set(r) - set(c))}"
+    assert {k: (c[k], r[k]) for k in c if c[k] != r[k]} == {}, "argument counts differ"
+
+
+def test_struct_fields_match_in_order():
+    c, r = c_structs(), rust_structs()
+    for name in ("rtiow_spheres", "rtiow_materials", "rtiow_camera", "rtiow_params", "rtiow_stats"):
+        assert c[name] == r[name], (name, c[name], r[name])
+    assert r["rtiow_ctx"] == []                                # opaque
+
+
+def test_constants_match():
+    h = _strip_c_comments(HDR)
+    consts = {m.group(1): int(m.group(2)) for m in re.finditer(r"\b(RTIOW_[A-Z0-9_]+)\s*=\s*(-?\d+)", h)}
+    consts.update({m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+(RTIOW_[A-Z0-9_]+)\s+(-?\d+)", h)})
+    rs = {m.group(1): int(m.group(2)) for m in re.finditer(r"pub const (RTIOW_[A-Z0-9_]+)\s*:\s*\w+\s*=\s*(-?\d+)\s*;", RS)}
+    assert consts["RTIOW_ABI_VERSION"] == rs["RTIOW_ABI_VERSION"] == 3
+    assert f"ABI version {consts['RTIOW_ABI_VERSION']}" in RS.splitlines()[0]
+    missing = {k for k in consts if k not in rs and k != "RTIOW_CUDA_H"}
+    assert not missing, f"constants of the header missing from lib.rs: {sorted(missing)}"
+    assert {k: (consts[k], rs[k]) for k in rs if k in consts and consts[k] != rs[k]} == {}
+
+
+def test_ctypes_binding_and_library_export_the_same_symbols(capi):
+    c = c_functions()
+    assert sorted(capi.SYMBOLS) == sorted(c)
+    L = capi.lib()
+    for name in c:
+        assert hasattr(L, name), f"librtiow_cuda.so does not export {name}"
+    assert L.rtiow_abi_version() == 3
