@@ -7,16 +7,18 @@
 
 A *step* is one full frame of the workload: BASELINE.json configs[1], the RTIOW Part 1 final scene
 (seeded random_scene, main.rs:59-102) at 1200x675, 500 spp, depth 50 — 405 M paths.  At N > 1 the same frame is
-split into interleaved row tiles, one rank per GPU ("strong" scaling); the tiles reach rank 0 either fused into the epilogue
-(stores into rank 0's frame over NVLink, torch symmetric memory — default when available, cross-checked against the other
-path in the same run) or through tile buffers + an NCCL all-gather (--gather nccl).
+split into interleaved row tiles, one rank per GPU ("strong" scaling), and gathered INSIDE librtiow_cuda.so
+(rtiow_ctx_create_rank + rtiow_render_rank: fused peer stores into rank 0's frame, or --gather nccl: ncclAllGather);
+torch.distributed only launches, hands out the library's NCCL id, and reduces the timings.
 
-  value     device-resident: scene already in HBM, tiles -> (all-gather) -> top-down frame left in HBM
-  e2e       the reference-facing call with HOST buffers: scene upload (H2D) + render + frame to host (D2H)
-  roofline  FP32 pipe: 17 FLOP x rays traced x spheres / render-kernel time, against an FFMA
-            calibration kernel run in this process (MEASURED_PEAKS.json has no FP32 entry)
+  value     device-resident: scene already in HBM, this rank's rows + gather, frame left in HBM (rtiow_render_rank_device)
+  e2e       the reference-facing call with HOST buffers: scene upload (H2D) + rtiow_render_rank + frame to host (D2H)
+  roofline  the dominant kernel against the tensor pipe (executed fp16 FLOP, MEASURED_PEAKS.json) when the filter runs on
+            tcgen05, else the FP32 pipe; roofline_fp32 always carries SURVEY §8(d)'s algorithmic figure
+            (17 FLOP x rays x spheres) against an FFMA2 calibration kernel run in this process
   cpu_baseline  the f64 CPU oracle (a port: the Rust reference cannot be built here) on a bounded sample
-  --impl reference  times that same CPU restatement, all host threads, as the reference arm
+  --impl reference  times that same CPU restatement, all host threads, as the reference arm (loads nothing of the product)
+  --inproc  one process, N GPUs: rtiow_ctx_create(N) + rtiow_render
 """
 from __future__ import annotations
 
@@ -70,8 +72,10 @@ def parse():
     ap.add_argument("--cpu-sample-spp", type=int, default=0, help="spp of the bounded CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather", default="auto", choices=["auto", "fused", "nccl"],
-                    help="N > 1: 'fused' = every rank's epilogue stores its pixels into rank 0's frame over NVLink (torch symmetric memory) and a "
-                         "device-side barrier follows; 'nccl' = tile buffers + NCCL all-gather + de-interleave; 'auto' = fused when available")
+                    help="N > 1, inside librtiow_cuda.so: 'nccl' = tile buffers + ncclAllGather + de-interleave; 'fused' = every rank's epilogue stores its "
+                         "pixels into rank 0's frame over NVLink (CUDA IPC mapping) + a 1-int NCCL all-reduce as barrier; 'auto' = fused when the mapping works")
+    ap.add_argument("--scan", default="auto", choices=["auto", "fp32", "tensor"], help="sphere filter backend (rtiow_ctx_set_scan_backend)")
+    ap.add_argument("--inproc", action="store_true", help="one process driving --gpus N devices through rtiow_ctx_create(N) + rtiow_render (no torchrun)")
     a = ap.parse_args()
     name, w, h, spp, grid, mode = CONFIGS[a.config]
     a.workload = name if (a.width, a.height, a.spp) == (None, None, None) else f"{name} [overridden size]"
@@ -121,10 +125,20 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+# ----------------------------------------------------------------------------------------------- shared
+def make_config(args, n_spheres):
+    """the workload, identical for both arms (the driver compares it): everything else goes to `impl_detail`"""
+    return {"workload": args.workload, "width": args.width, "height": args.height, "spp": args.spp, "max_depth": WORKLOAD["max_depth"],
+            "n_spheres": n_spheres, "scene_seed": WORKLOAD["scene_seed"], "sample_seed": WORKLOAD["sample_seed"]}
+
+
 # ----------------------------------------------------------------------------------------------- CPU arms
-def oracle_world(scene_arrays):
-    from oracle import oracle as o            # the checker / CPU baseline: bench.py is one of the places allowed to load it
-    return o, o.Scene(**scene_arrays)
+def oracle_module(native=True):
+    """the checker / CPU baseline: bench.py is one of the places allowed to load oracle/.  For the TIMED legs the oracle is
+    rebuilt with -march=native on this box (the committed recipe targets baseline x86-64 because the .so travels)."""
+    from oracle import oracle as o
+    march = "native" if (native and o.use_native_build()) else "x86-64"
+    return o, march
 
 
 def time_oracle(o, sc, W, H, spp, seed):
@@ -138,12 +152,13 @@ def time_oracle(o, sc, W, H, spp, seed):
 
 def run_reference(args, rank):
     """Reference arm: the reference's own CPU implementation of the path, all host threads.
-    rustc/cargo are absent, so this is the oracle port (oracle/rtiow_oracle.c, OpenMP rows like rayon-per-row)."""
+    rustc/cargo are absent, so this is the oracle port (oracle/rtiow_oracle.c, OpenMP rows like rayon-per-row).  Nothing of the
+    product is loaded: the world comes from the host-only scene library under oracle/build/."""
     if rank != 0:
         return
-    from rtiow_b200 import capi
+    o, march = oracle_module()
     W, H = args.width, args.height
-    o, sc = oracle_world(capi.random_scene(WORKLOAD["scene_seed"], args.grid, args.material_mode))
+    sc = o.Scene(**o.random_scene(WORKLOAD["scene_seed"], args.grid, args.material_mode))
     spp = args.cpu_sample_spp or (4 if sc.n < 2000 else 1)
     cores = o.host_threads()
     for _ in range(args.warmup):
@@ -153,19 +168,63 @@ def run_reference(args, rank):
         time_oracle(o, sc, W, H, spp, 1 + k)
     dt = time.perf_counter() - t0
     v = W * H * spp * args.steps / dt / 1e6
-    sample = f"{W}x{H} @ {spp} spp per step ({W * H * spp / 1e6:.2f} M paths) of the {args.spp} spp workload; rate is spp-independent"
+    sample = (f"each step renders {W}x{H} @ {spp} spp ({W * H * spp / 1e6:.2f} M paths) of the {args.spp} spp workload; Mpaths/s does not depend on spp; "
+              f"f64 C restatement (gcc -O2 -march={march}, OpenMP rows), NOT `cargo run --release`: no rustc in this image")
     emit_json({
         "impl": "reference", "metric": "Mpaths/s", "value": v, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": {"workload": args.workload, "width": W, "height": H, "spp": args.spp,
-                                                          "max_depth": 50, "n_spheres": sc.n, "scene_seed": 1},
+        "dtype": "f64", "data": "synthetic", "config": make_config(args, sc.n),
         "cpu_baseline": {"value": v, "unit": "Mpaths/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-        "note": "CPU restatement of main.rs:122-145 (f64, gcc -O2, OpenMP rows); NOT `cargo run --release`: no rustc in this image"})
+        "gpu_launches": 0})
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
+def roofline_objects(world, kms, rays_total, n_spheres, npad, backend_tensor, peak_fp32, peak_fp32_scalar, args, paths, kernel_name):
+    """Two rooflines for the dominant kernel (per GPU).  The filter's work is `rays x spheres` discriminants:
+      fp32  : the ALGORITHMIC figure of SURVEY §8(d), 17 FLOP per test, against the FP32 pipe (FFMA2 calibration kernel of this run).
+              With the filter on the tensor cores this exceeds 1: the FP32 pipe no longer does that work.
+      tensor: the FLOP the tensor cores EXECUTE: per test 3 products (hi.hi, hi.lo, lo.hi) x K = 16 x 2 = 96, padding spheres
+              included, against the measured dense bf16/fp16 peak of MEASURED_PEAKS.json (sustained: the kernel is the whole step).
+    """
+    tests_alg = rays_total * n_spheres / world
+    fp32 = {"bound": "fp32", "achieved": tests_alg * FLOP_PER_TEST / (kms * 1e-3) / 1e12, "peak": peak_fp32, "unit": "TFLOP/s",
+            "flop_per_test": FLOP_PER_TEST, "sphere_tests_per_launch": tests_alg, "peak_scalar_ffma": peak_fp32_scalar, "peak_nominal": FP32_NOMINAL_TFLOPS,
+            "peak_source": "FFMA2 calibration kernel in this run (rtiow_fp32_peak_probe); MEASURED_PEAKS.json has no FP32 entry",
+            "note": "algorithmic FLOP (SURVEY §8d) over the FP32-pipe peak" + ("; > 1 is expected: the filter runs on the tensor cores" if backend_tensor else "")}
+    fp32["frac"] = fp32["achieved"] / peak_fp32
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except (OSError, ValueError):
+        pass
+    t_peak, t_src = peaks.get("bf16_tflops_sustained"), "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16 8192^3, back to back; fp16 runs at the same rate)"
+    if not t_peak:
+        t_peak, t_src = 1400.0, "fallback of B200_PROFILING.md (sustained ~1.4 PFLOP/s); MEASURED_PEAKS.json absent"
+    traffic, t_note = None, "no ncu under bench.py; see profiles/ for the capture of this kernel"
+    side = ROOT / "profiles" / "r2_dram_bytes.json"
+    if side.exists():
+        try:
+            rec = json.loads(side.read_text()).get(f"{args.config}:{kernel_name}")
+            if rec and world == 1 and (args.width, args.height, args.spp) == tuple(rec["frame"]):
+                traffic, t_note = rec["dram_bytes"], rec["source"]
+        except (ValueError, KeyError):
+            pass
+    if backend_tensor:
+        flop_exec = rays_total * npad * 96.0 / world
+        main = {"bound": "tensor", "achieved": flop_exec / (kms * 1e-3) / 1e12, "peak": t_peak, "unit": "TFLOP/s", "peak_source": t_src,
+                "peak_burst": peaks.get("bf16_tflops"), "flop_per_test_executed": 96.0, "spheres_padded": npad,
+                "bound_note": "the sphere filter is a [rays x 11] x [11 x spheres] contraction on tcgen05 (fp16 hi/lo split, 3 MMAs of K = 16 per chunk, fp32 "
+                              "accumulate in TMEM); what actually limits the kernel is the sign collection on the half-rate ALU pipe (1 SHF per test) and the "
+                              "latency of the per-ray code, see DESIGN.md §1.2 and profiles/"}
+        main["frac"] = main["achieved"] / t_peak
+    else:
+        main = dict(fp32)
+    main.update({"traffic": traffic, "traffic_unit": "bytes/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)", "traffic_note": t_note,
+                 "kernel": kernel_name, "kernel_ms": kms, "rays_per_path": rays_total / paths})
+    return main, fp32
+
+
 def run_ours(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -174,133 +233,62 @@ def run_ours(args, rank, local_rank, world):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the render path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    nccl_id = None
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # torch.distributed is the launcher's plumbing only: rendezvous, the NCCL unique id of the LIBRARY's communicator, the
+        # barrier around the timed region and the max over ranks.  Tiles never pass through torch: the gather is inside
+        # librtiow_cuda.so (rtiow_render_rank*).
+        dist.init_process_group("nccl", device_id=dev)
+        box = [capi.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        nccl_id = box[0]
     W, H, spp = args.width, args.height, args.spp
     scene = capi.random_scene(WORKLOAD["scene_seed"], args.grid, args.material_mode)
     n_spheres = len(scene["radius"])
-    ctx = capi.Context(device=local_rank)
+    ctx = capi.Context(device=local_rank, rank=rank, world=world, nccl_id=nccl_id)
+    ctx.set_gather({"auto": capi.GATHER_AUTO, "fused": capi.GATHER_FUSED, "nccl": capi.GATHER_NCCL}[args.gather])
+    ctx.set_scan_backend({"auto": capi.SCAN_AUTO, "fp32": capi.SCAN_FP32, "tensor": capi.SCAN_TENSOR}[args.scan])
     ctx.upload_scene(**scene)
     cam = capi.camera_new((13, 2, 3), (0, 0, 0), (0, 1, 0), 20.0, W / H, 0.1, 10.0)
     prm = capi.default_params(width=W, height=H, spp=spp, max_depth=WORKLOAD["max_depth"], t_min=WORKLOAD["t_min"], seed=WORKLOAD["sample_seed"],
                               tile_rows=args.tile_rows)
-    tile_bytes = ctx.tile_buffer_bytes(prm, world)
-    dev = torch.device("cuda", local_rank)
-    tiles = torch.empty(tile_bytes, dtype=torch.uint8, device=dev)
-    gathered = torch.empty(tile_bytes * world, dtype=torch.uint8, device=dev) if world > 1 else tiles
-    frame = torch.empty(W * H * 4, dtype=torch.uint8, device=dev)
-    host_frame = torch.empty(W * H * 4, dtype=torch.uint8).pin_memory()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)        # > 126 MB L2
-    # One dedicated stream for everything: the library's launches (it gets the raw handle), torch's fills and copies, NCCL's
-    # stream dependencies and the timing events.  (The legacy default stream has handle 0, which the C ABI reads as "use the
-    # context's own stream" — work there would not be ordered against torch's.)
+    # One stream for everything: the library works on it (rtiow_ctx_set_stream), so torch's L2-flush fills and the timing events
+    # are ordered with the library's kernels and NCCL calls.
     stream = torch.cuda.Stream(dev)
     torch.cuda.set_stream(stream)
-    sp = stream.cuda_stream
-    assert sp != 0
-    launches = [0]
+    ctx.set_stream(stream.cuda_stream)
+    host_np = np.empty((H, W, 4), np.uint8)
 
-    # N > 1, the gather.  Preferred: FUSED into the epilogue — rank 0's frame lives in symmetric memory (mapped into every rank's
-    # address space over NVLink), finalize_to_frame_kernel of each rank stores its rows straight into it, and a device-side barrier
-    # (signal pads, on the stream) tells rank 0 the frame is complete.  Fallback / cross-check: tile buffers + NCCL all-gather +
-    # de-interleave kernel, which is what north_star names.
-    fused, hdl, frame_sym, frame0_ptr, gather_note = False, None, None, 0, "single GPU"
-    if world > 1:
-        ok = 0
-        if args.gather in ("auto", "fused"):
-            try:
-                import torch.distributed._symmetric_memory as symm
-                frame_sym = symm.empty(W * H * 4, dtype=torch.uint8, device=dev)
-                hdl = symm.rendezvous(frame_sym, dist.group.WORLD)
-                frame0_ptr = int(hdl.buffer_ptrs[0])
-                ok = 1
-            except Exception as e:            # no P2P / symmetric-memory support on this box
-                gather_note = f"NCCL all-gather (symmetric memory unavailable: {type(e).__name__})"
-        t_ok = torch.tensor([ok], dtype=torch.int32, device=dev)
-        dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
-        fused = bool(t_ok.item())
-        if args.gather == "fused" and not fused:
-            raise SystemExit("bench.py: --gather fused requested but torch symmetric memory is not available")
-        if not fused and args.gather != "auto":
-            gather_note = "NCCL all-gather"
-
-    def step_nccl(stats=False):
-        """tiles -> all-gather -> de-interleave, everything stays in HBM"""
-        st = ctx.render_tiles_device(cam, prm, rank, world, tiles.data_ptr(), sp, want_stats=stats)
-        launches[0] += 2
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, tiles)
-            ctx.deinterleave_device(gathered.data_ptr(), prm, world, frame.data_ptr(), sp)
-            launches[0] += 1
+    def step_device():
+        """this rank's rows + the gather, frame left in HBM (rank 0)"""
+        _, st = ctx.render_rank_device(cam, prm)
         return st
-
-    def step_fused(stats=False):
-        """every rank's epilogue stores into rank 0's frame (peer memory), then a device-side barrier on the stream"""
-        st = ctx.render_to_frame_device(cam, prm, rank, world, frame0_ptr, sp, want_stats=stats)
-        launches[0] += 2
-        hdl.barrier(channel=0)
-        return st
-
-    if fused:                                 # cross-check once: the fused frame must equal the NCCL-gathered one, byte for byte
-        step_nccl(); step_fused(); torch.cuda.synchronize(dev)
-        same = torch.tensor([1 if (rank != 0 or torch.equal(frame_sym, frame)) else 0], dtype=torch.int32, device=dev)
-        dist.all_reduce(same, op=dist.ReduceOp.MIN)
-        if not bool(same.item()):             # never seen; if it happens the timed path is the one north_star names
-            if rank == 0:
-                a, b = frame_sym.view(H, W, 4), frame.view(H, W, 4)
-                bad_rows = (a != b).any(dim=2).any(dim=1).nonzero().flatten().tolist()
-                print(f"bench.py: fused gather != NCCL all-gather on {len(bad_rows)} rows (first {bad_rows[:8]}): falling back to NCCL", file=sys.stderr)
-            if args.gather == "fused":
-                raise SystemExit("bench.py: fused gather and NCCL all-gather disagree")
-            fused = False
-            gather_note = "NCCL all-gather (the fused gather failed its cross-check on this box)"
-    if fused:
-        gather_note = "epilogue stores into rank 0's frame over NVLink (torch symmetric memory) + device-side barrier; verified byte-identical to tiles + NCCL all-gather + de-interleave"
-    step_device = step_fused if fused else step_nccl
 
     def step_e2e():
         """what a caller of the C ABI does per frame, from host buffers to host buffers"""
         ctx.upload_scene(**scene)                                                  # H2D: the scene SoA
-        if world == 1:
-            img, st = ctx.render(cam, prm, out=host_np)                            # D2H inside rtiow_render
-            launches[0] += 2
-            return st
-        if fused:
-            st = step_fused(stats=True)
-            if rank == 0:
-                host_frame.copy_(frame_sym, non_blocking=True)
-            stream.synchronize()
-            return st
-        st = ctx.render_tiles_device(cam, prm, rank, world, tiles.data_ptr(), sp, want_stats=True)
-        dist.all_gather_into_tensor(gathered, tiles)
-        launches[0] += 2
-        if rank == 0:
-            ctx.deinterleave_device(gathered.data_ptr(), prm, world, frame.data_ptr(), sp)
-            host_frame.copy_(frame, non_blocking=True)
-            launches[0] += 1
-        stream.synchronize()
+        _, st = ctx.render_rank(cam, prm, out=host_np if rank == 0 else None)      # rank 0: D2H of the frame inside the call
         return st
-
-    host_np = host_frame.numpy().reshape(H, W, 4)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def maxr(x):
+    def reduce(x, op):
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
+    def maxr(x):
+        return reduce(x, dist.ReduceOp.MAX if world > 1 else None)
+
     def sumr(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        return reduce(x, dist.ReduceOp.SUM if world > 1 else None)
 
     # FP32-pipe calibration, same process, same clocks regime (a kernel of about the step's length)
     peak_tflops, _ = ctx.fp32_peak_probe(packed=True, target_ms=300.0)
@@ -308,25 +296,26 @@ def run_ours(args, rank, local_rank, world):
 
     for _ in range(args.warmup):
         flush.fill_(1)
-        step_device(stats=True)
+        st = step_device()
     barrier()
+    gather_note = ctx.gather_info()
+    per_step_launches = st["kernel_launches"]                                       # render + finalize (+ de-interleave): OUR kernels, not NCCL's
+    backend_tensor = st["scan_backend"] == capi.SCAN_TENSOR
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    launches[0] = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kernel_ms, rays = [], []
     barrier()
     e0.record(stream)
     for _ in range(args.steps):
         flush.fill_(1)                                                             # evict L2 between timed iterations
-        st = step_device(stats=True)
+        st = step_device()
         kernel_ms.append(st["kernel_ms"]); rays.append(st["rays_traced"])
     e1.record(stream)
     barrier()
     total_ms = maxr(e0.elapsed_time(e1))
     clk = clocks.stop() if rank == 0 else None
-    n_launch = launches[0]
     ms_per_step = total_ms / args.steps
     paths = W * H * spp
     value = paths / (ms_per_step * 1e-3) / 1e6
@@ -339,49 +328,83 @@ def run_ours(args, rank, local_rank, world):
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        st_e = step_e2e()
+        step_e2e()
     torch.cuda.synchronize(dev)
     e2e_ms = maxr((time.perf_counter() - t0) * 1e3) / args.steps
     barrier()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        o, sc = oracle_world(scene)
+        o, march = oracle_module()
+        sc = o.Scene(**scene)
         cores = o.host_threads()
         s_spp = args.cpu_sample_spp or max(1, min(spp, int(2 * cores * (1200 * 675) / (W * H) * 530 / n_spheres)))   # ~10-30 s of CPU work
         v, dt, _ = time_oracle(o, sc, W, H, s_spp, 1)
         cpu = {"value": v, "unit": "Mpaths/s", "cores": cores, "kind": "port",
-               "sample": f"{W}x{H} @ {s_spp} spp ({W * H * s_spp / 1e6:.1f} M paths, {dt:.1f} s) of the {spp} spp workload; f64 C restatement, OpenMP rows"}
+               "sample": f"{W}x{H} @ {s_spp} spp ({W * H * s_spp / 1e6:.1f} M paths, {dt:.1f} s) of the {spp} spp workload; f64 C restatement (gcc -O2 -march={march}), OpenMP rows"}
 
     if rank == 0:
-        flops = rays_total * n_spheres * FLOP_PER_TEST                             # per frame, all GPUs
-        achieved = flops / (kms * 1e-3) / 1e12 / world                             # per GPU
+        # the spheres the filter sees: |r| <= 8 and |c| + |r| <= 4096 (capi.cu: the others go to the f64 list), padded to whole MMA chunks
+        reach = np.linalg.norm(scene["center"], axis=1) + np.abs(scene["radius"])
+        n_small = int(((np.abs(scene["radius"]) <= 8.0) & (reach <= 4096.0)).sum())
+        npad = -(-max(n_small, 1) // 64) * 64 if backend_tensor else n_spheres
+        kname = "rt::render_kernel_umma<6,64>" if backend_tensor else ("rt::render_kernel<float,true,256,3>" if n_spheres < 3000 else "rt::render_kernel<float,true,768,1>")
+        roof, roof32 = roofline_objects(world, kms, rays_total, n_spheres, npad, backend_tensor, peak_tflops, peak_scalar_tflops, args, paths, kname)
         scene_bytes = sum(int(np.asarray(v).nbytes) for v in scene.values())
         out = {
             "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "width": W, "height": H, "spp": spp, "max_depth": WORKLOAD["max_depth"], "n_spheres": n_spheres,
-                       "scene_seed": WORKLOAD["scene_seed"], "sample_seed": WORKLOAD["sample_seed"], "tile_rows": args.tile_rows,
-                       "parallelism": f"interleaved row tiles x{world}" + (f", {gather_note}" if world > 1 else ""),
-                       "l2": "256 MiB device buffer rewritten between timed steps (inside the timed region, ~0.1 ms)"},
+            "config": make_config(args, n_spheres),
+            "impl_detail": {"tile_rows": args.tile_rows, "scan_backend": "tensor (tcgen05)" if backend_tensor else "fp32 (FFMA2)",
+                            "parallelism": f"interleaved row tiles x{world}; {gather_note}",
+                            "l2": "256 MiB device buffer rewritten between timed steps (inside the timed region, ~0.1 ms)"},
             "clocks": clk,
             "e2e": {"value": paths / (e2e_ms * 1e-3) / 1e6, "unit": "Mpaths/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": scene_bytes + 176 + 48, "d2h_bytes_per_step": W * H * 4 + 16},
-            "gpu_launches": n_launch,
-            "roofline": {"bound": "fp32", "bound_note": "FP32 CUDA-core pipe (north_star's roofline): the scan is 7 packed FFMA2 per sphere pair out of shared memory; "
-                                                        "HBM traffic is ~20 MB per 9.7 TFLOP launch and tensor cores do not apply (no contraction)",
-                         "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
-                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (world == 1 and args.config == "cfg2" and (W, H, spp) == (1200, 675, 500)) else None, "traffic_unit": "bytes/launch (ncu)",
-                         "kernel": "rt::render_kernel<float,true,256,3>" if n_spheres < 2500 else "rt::render_kernel<float,true,768,1>", "kernel_ms": kms, "flop_per_test": FLOP_PER_TEST,
-                         "rays_per_path": rays_total / paths, "sphere_tests_per_launch": rays_total * n_spheres / world,
-                         "peak_source": "FFMA2 calibration kernel in this run (rtiow_fp32_peak_probe, ~300 ms); MEASURED_PEAKS.json has no FP32 entry",
-                         "peak_scalar_ffma": peak_scalar_tflops, "peak_nominal": FP32_NOMINAL_TFLOPS},
+                    "h2d_bytes_per_step": scene_bytes + 176 + 48, "d2h_bytes_per_step": W * H * 4 + 16,
+                    "call": "rtiow_scene_upload + rtiow_render_rank (host buffers; gather inside the library)"},
+            "gpu_launches": per_step_launches * args.steps,
+            "roofline": roof, "roofline_fp32": roof32,
         }
         if cpu:
             out["cpu_baseline"] = cpu
         emit_json(out)
     if world > 1:
         dist.destroy_process_group()
+    ctx.close()
+
+
+def run_inproc(args):
+    """One process driving N GPUs through rtiow_ctx_create(N) + rtiow_render — what `render(n_gpus)` of the Rust / C++ host calls
+    (INTEGRATION.md).  No torch, no torch.distributed.  Host buffers in and out; wall clock around K calls."""
+    from rtiow_b200 import capi
+    W, H, spp, n = args.width, args.height, args.spp, args.gpus
+    scene = capi.random_scene(WORKLOAD["scene_seed"], args.grid, args.material_mode)
+    ctx = capi.Context(n)
+    ctx.set_gather({"auto": capi.GATHER_AUTO, "fused": capi.GATHER_FUSED, "nccl": capi.GATHER_NCCL}[args.gather])
+    ctx.set_scan_backend({"auto": capi.SCAN_AUTO, "fp32": capi.SCAN_FP32, "tensor": capi.SCAN_TENSOR}[args.scan])
+    ctx.upload_scene(**scene)
+    cam = capi.camera_new((13, 2, 3), (0, 0, 0), (0, 1, 0), 20.0, W / H, 0.1, 10.0)
+    prm = capi.default_params(width=W, height=H, spp=spp, max_depth=WORKLOAD["max_depth"], t_min=WORKLOAD["t_min"], seed=WORKLOAD["sample_seed"], tile_rows=args.tile_rows)
+    out = np.empty((H, W, 4), np.uint8)
+    for _ in range(args.warmup):
+        _, st = ctx.render(cam, prm, out=out)
+    clocks = ClockSampler(0); clocks.start()
+    kms = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.flush_l2()
+        _, st = ctx.render(cam, prm, out=out)
+        kms.append(st["kernel_ms"])
+    dt = (time.perf_counter() - t0) / args.steps
+    clk = clocks.stop()
+    paths = W * H * spp
+    emit_json({"impl": "ours-inproc", "metric": "Mpaths/s", "value": paths / dt / 1e6, "unit": "Mpaths/s", "n_gpus": n, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": make_config(args, len(scene["radius"])),
+               "impl_detail": {"tile_rows": args.tile_rows, "parallelism": ctx.gather_info(), "timing": "host wall clock around rtiow_flush_l2 + rtiow_render (host frame out), K calls",
+                               "kernel_ms_slowest_device": float(np.mean(kms)), "rays_per_path": st["rays_traced"] / paths},
+               "clocks": clk, "gpu_launches": st["kernel_launches"] * args.steps,
+               "e2e": {"value": paths / dt / 1e6, "unit": "Mpaths/s", "h2d_bytes_per_step": 176 + 48, "d2h_bytes_per_step": W * H * 4 + 16}})
     ctx.close()
 
 
@@ -412,7 +435,10 @@ def main():
     rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    if args.gpus > 1 and world == 1:
+    if args.inproc:
+        claim_stdout()
+        return run_inproc(args)
+    if args.gpus > 1 and world == 1 and args.impl == "ours":
         # convenience: relaunch under torchrun, one rank per GPU
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", "29517", __file__] + sys.argv[1:]

@@ -133,6 +133,9 @@ int  rtiow_ctx_set_scan_backend(rtiow_ctx* ctx, int backend);
  * (libnccl.so.2); if it is missing these return RTIOW_ERR_NCCL. */
 int  rtiow_nccl_unique_id(void* out_id);
 int  rtiow_ctx_create_rank(int device, int rank, int world, const void* nccl_unique_id, rtiow_ctx** out);
+/* a one-device ctx works on the caller's cudaStream_t from now on (NULL: back to its own stream), so the caller's events and
+ * copies on that stream are ordered with the library's kernels and collectives */
+int  rtiow_ctx_set_stream(rtiow_ctx* ctx, void* stream);
 /* rtiow_gather_mode of every later multi-GPU render on this ctx (an n-GPU ctx or a rank ctx) */
 int  rtiow_ctx_set_gather(rtiow_ctx* ctx, int mode);
 /* one line describing the gather the last render used (for logs and bench lines) */

@@ -29,7 +29,7 @@ PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint3
 # every symbol include/rtiow_cuda.h declares (tests check the .so exports exactly these)
 SYMBOLS = [
     "rtiow_abi_version", "rtiow_last_error", "rtiow_device_count", "rtiow_ctx_create", "rtiow_ctx_create_on_device",
-    "rtiow_ctx_destroy", "rtiow_ctx_set_scan_backend", "rtiow_nccl_unique_id", "rtiow_ctx_create_rank", "rtiow_ctx_set_gather",
+    "rtiow_ctx_destroy", "rtiow_ctx_set_scan_backend", "rtiow_nccl_unique_id", "rtiow_ctx_create_rank", "rtiow_ctx_set_gather", "rtiow_ctx_set_stream",
     "rtiow_ctx_gather_info", "rtiow_render_rank", "rtiow_render_rank_device", "rtiow_scene_upload", "rtiow_camera_new", "rtiow_params_default", "rtiow_render", "rtiow_render_progressive",
     "rtiow_tile_buffer_bytes", "rtiow_render_tiles_device", "rtiow_render_to_frame_device", "rtiow_deinterleave_device", "rtiow_sphere_hit_batch",
     "rtiow_hitlist_batch", "rtiow_scatter_batch", "rtiow_get_ray_batch", "rtiow_to_rgba_batch", "rtiow_reflect_batch",
@@ -111,6 +111,7 @@ def _declare(L):
         "rtiow_nccl_unique_id": (C.c_int, [P]),
         "rtiow_ctx_create_rank": (C.c_int, [C.c_int, C.c_int, C.c_int, P, C.POINTER(P)]),
         "rtiow_ctx_set_gather": (C.c_int, [P, C.c_int]),
+        "rtiow_ctx_set_stream": (C.c_int, [P, P]),
         "rtiow_ctx_gather_info": (C.c_int, [P, C.c_char_p, C.c_size_t]),
         "rtiow_render_rank": (C.c_int, [P, C.POINTER(Camera), C.POINTER(Params), P, C.POINTER(Stats)]),
         "rtiow_render_rank_device": (C.c_int, [P, C.POINTER(Camera), C.POINTER(Params), C.POINTER(P), C.POINTER(Stats)]),
@@ -265,6 +266,10 @@ class Context:
     def set_gather(self, mode: int):
         """GATHER_AUTO / GATHER_NCCL (tile buffers + ncclAllGather + de-interleave) / GATHER_FUSED (peer stores into rank 0's frame)"""
         _check(lib().rtiow_ctx_set_gather(self._h, mode))
+
+    def set_stream(self, stream_ptr: int):
+        """a one-device ctx works on this cudaStream_t from now on (0: back to its own)"""
+        _check(lib().rtiow_ctx_set_stream(self._h, C.c_void_p(stream_ptr)))
 
     def gather_info(self) -> str:
         buf = C.create_string_buffer(512)

@@ -73,7 +73,7 @@ template <typename U> struct DevBuf {
 struct DeviceState {
     int device = 0;
     int sms = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr; bool owns_stream = true;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_done = nullptr;
     // scene
     DevBuf<float> table; DevBuf<float4> small; DevBuf<int> small_idx; DevBuf<double4> big; DevBuf<int> big_idx;
@@ -260,6 +260,21 @@ extern "C" int rtiow_ctx_create_rank(int device, int rank, int world, const void
     return RTIOW_OK;
 }
 
+// A one-device ctx does all its work on `stream` from now on (a cudaStream_t the caller owns; NULL restores the ctx's own):
+// the caller's events and copies on that stream are then ordered with the library's kernels and NCCL calls.
+extern "C" int rtiow_ctx_set_stream(rtiow_ctx* c, void* stream)
+{
+    if (!c) return fail(RTIOW_ERR_INVALID_ARG, "ctx is NULL");
+    if (c->dev.size() != 1) return fail(RTIOW_ERR_INVALID_ARG, "rtiow_ctx_set_stream needs a one-device ctx");
+    DeviceState& d = c->dev[0];
+    CU(cudaSetDevice(d.device));
+    CU(cudaStreamSynchronize(d.stream));
+    if (d.owns_stream && d.stream) cudaStreamDestroy(d.stream);
+    if (stream) { d.stream = (cudaStream_t)stream; d.owns_stream = false; }
+    else { CU(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking)); d.owns_stream = true; }
+    return RTIOW_OK;
+}
+
 extern "C" int rtiow_ctx_set_gather(rtiow_ctx* c, int mode)
 {
     if (!c) return fail(RTIOW_ERR_INVALID_ARG, "ctx is NULL");
@@ -309,7 +324,7 @@ extern "C" void rtiow_ctx_destroy(rtiow_ctx* c)
         if (d.ev0) cudaEventDestroy(d.ev0);
         if (d.ev1) cudaEventDestroy(d.ev1);
         if (d.ev_done) cudaEventDestroy(d.ev_done);
-        if (d.stream) cudaStreamDestroy(d.stream);
+        if (d.stream && d.owns_stream) cudaStreamDestroy(d.stream);
     }
     delete c;
 }

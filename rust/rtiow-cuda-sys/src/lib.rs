@@ -96,6 +96,7 @@ extern "C" {
     pub fn rtiow_ctx_set_scan_backend(ctx: *mut rtiow_ctx, backend: c_int) -> c_int;
     pub fn rtiow_nccl_unique_id(out_id: *mut c_void) -> c_int;
     pub fn rtiow_ctx_create_rank(device: c_int, rank: c_int, world: c_int, nccl_unique_id: *const c_void, out: *mut *mut rtiow_ctx) -> c_int;
+    pub fn rtiow_ctx_set_stream(ctx: *mut rtiow_ctx, stream: *mut c_void) -> c_int;
     pub fn rtiow_ctx_set_gather(ctx: *mut rtiow_ctx, mode: c_int) -> c_int;
     pub fn rtiow_ctx_gather_info(ctx: *mut rtiow_ctx, buf: *mut c_char, n: usize) -> c_int;
     pub fn rtiow_scene_upload(ctx: *mut rtiow_ctx, spheres: *const rtiow_spheres, materials: *const rtiow_materials) -> c_int;
