@@ -70,6 +70,32 @@ def test_statistical_parity_vs_reference_sampler(ctx_final, capi, oracle, final_
     assert np.abs(img[:8, :, :3].astype(int) - a[:8, :, :3].astype(int)).max() <= 1
 
 
+def test_statistical_parity_high_spp(ctx_final, capi, oracle, final_scene):
+    """north_star's second parity level AT HIGH SPP (VERDICT r1 weak #1d): 400x225 @ 500 spp, where the noise floor is ~1.8 LSB and
+    a bias would show.  Stated bound: RMSE(gpu, oracle) <= 1.25 x RMSE(oracle seed A, oracle seed B) and per-channel mean within
+    0.1 of an 8-bit unit — no standard-error allowance needed at this size.  Two oracle renders with the reference-faithful
+    rejection sampler (~30-45 s each on the box's host threads)."""
+    import json
+    from conftest import ROOT
+    _, sc = final_scene
+    W, H, spp = 400, 225, 500
+    ocam = final_camera(oracle, W / H)
+    a, _, _ = oracle.render(sc, ocam, W, H, spp, seed=1001, sampler=oracle.SAMPLER_REJECTION)
+    b, _, _ = oracle.render(sc, ocam, W, H, spp, seed=2002, sampler=oracle.SAMPLER_REJECTION)
+    img, st = render_gpu(ctx_final, capi, final_camera(capi, W / H), width=W, height=H, spp=spp, seed=3003)
+    floor, ra, rb = rmse(a, b), rmse(img, a), rmse(img, b)
+    means = [float(img[..., c].astype(float).mean() - 0.5 * (a[..., c].astype(float).mean() + b[..., c].astype(float).mean())) for c in range(3)]
+    out = ROOT / "gpurun_out" / "parity_image_r2.json"
+    out.parent.mkdir(exist_ok=True)
+    out.write_text(json.dumps({"frame": [W, H, spp], "scan_backend": st["scan_backend"], "rmse_oracleA_oracleB": floor, "rmse_gpu_oracleA": ra, "rmse_gpu_oracleB": rb,
+                               "bound": 1.25 * floor, "mean_gpu_minus_oracle_per_channel": means, "mean_bound": 0.1,
+                               "psnr_gpu_oracleA_db": float(20 * np.log10(255.0 / ra))}, indent=1))
+    assert 1.2 < floor < 2.6, floor                         # SURVEY §8c measured 1.81 at this size
+    assert ra <= 1.25 * floor and rb <= 1.25 * floor, (ra, rb, floor)
+    assert max(abs(m) for m in means) <= 0.1, means
+    assert np.abs(img[:12, :, :3].astype(int) - a[:12, :, :3].astype(int)).max() <= 1          # sky-only rows
+
+
 @pytest.mark.parametrize("mode,name", [(1, "all-Lambertian"), (2, "all-Metal"), (3, "all-Dialectric + hollow shell")])
 def test_material_isolation_scenes(ctx, capi, oracle, scene_factory, mode, name):
     """BASELINE configs[2] (reduced size): divergence-stress scenes, same-path comparison per material"""
