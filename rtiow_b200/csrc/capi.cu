@@ -1383,6 +1383,19 @@ extern "C" int rtiow_fp32_peak_probe(rtiow_ctx* c, int packed, double target_ms,
     return RTIOW_OK;
 }
 
+#ifdef RT_UMMA_TRACE
+// debug builds only: the clock stamps of the last render (tools/umma_trace.py); not declared in the public header
+extern "C" int rtiow_debug_umma_trace(long long* out, int cap)
+{
+    int n = 0;
+    cudaMemcpyFromSymbol(&n, rt::g_umma_trace_n, sizeof n);
+    n = std::min(n, cap);
+    cudaMemcpyFromSymbol(out, rt::g_umma_trace, (size_t)n * 2 * sizeof(long long));
+    int zero = 0; cudaMemcpyToSymbol(rt::g_umma_trace_n, &zero, sizeof zero);
+    return n;
+}
+#endif
+
 extern "C" int rtiow_flush_l2(rtiow_ctx* c)
 {
     if (!c) return fail(RTIOW_ERR_INVALID_ARG, "ctx is NULL");

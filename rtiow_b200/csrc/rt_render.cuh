@@ -322,8 +322,11 @@ __global__ void __launch_bounds__(G * 160, 1) render_kernel_umma(const RenderArg
         WorkCursor wc;
         for (;;) {
             uint32_t px = 0, pj = 0;
+            RT_STAMP(1);
             const bool fresh = assign_work(a, wc, lt_mask, pending, ps, acc_lp, &px, &pj);
+            RT_STAMP(2);
             if (!umma_group_any(ux, fresh || pending)) { umma_group_quit(ux); break; }
+            RT_STAMP(3);
 
             const Uniform4<float> u = event_uniforms<float>(a.key, ps.pix_key, ps.smp, fresh ? 0u : (uint32_t)(a.max_depth - ps.depth) + 1u);
             float sa, sb, z; event_sample(fresh, u, &sa, &sb, &z);
@@ -342,7 +345,9 @@ __global__ void __launch_bounds__(G * 160, 1) render_kernel_umma(const RenderArg
             pending = false;
 
             n_rays_w += __popc(__ballot_sync(RT_FULL, active));              // world.hit call count (main.rs:44)
+            RT_STAMP(4);
             const HitF h = closest_hit_umma<G, NC, RT_UMMA_EW>(ux, a.scene, ps.o, ps.dhat, ps.tmin_n, ps.self_code, ps.self_n);
+            RT_STAMP(9);
             if (active) {
                 if (h.idx < 0) accumulate(a, acc_lp, ps.thr * sky<float, true>(ps.dhat));                    // miss: sky (main.rs:54-56)
                 else { ps.o = ps.o + ps.dhat * h.t; hit_idx = h.idx; hit_code = h.code; pending = true; }    // ray.rs:15-17

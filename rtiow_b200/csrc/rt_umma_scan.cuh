@@ -49,6 +49,17 @@ template <int G, int NC> struct UmmaShape {
     }
 };
 
+// Debug builds only (-DRT_UMMA_TRACE, tools/umma_trace.py): clock stamps of block 0, warp 0 for the first iterations of the render
+// loop, so that the phases of an iteration (work assignment, group vote, per-ray code, feature rows, large spheres, each chunk's
+// wait / load / sign collection, candidate drain) can be read off in cycles.
+#ifdef RT_UMMA_TRACE
+__device__ long long g_umma_trace[4096];
+__device__ int g_umma_trace_n;
+#define RT_STAMP(tag) do { if (blockIdx.x == 0 && threadIdx.x == 0) { int i_ = g_umma_trace_n; if (i_ < 2040) { g_umma_trace[2 * i_] = (tag); g_umma_trace[2 * i_ + 1] = clock64(); g_umma_trace_n = i_ + 1; } } } while (0)
+#else
+#define RT_STAMP(tag) do { } while (0)
+#endif
+
 // per-thread view of its group's resources
 struct UmmaCtx {
     uint32_t t_d, t_a;              // TMEM columns of the group's D and A (A_hi at t_a, A_lo at t_a + 8); lane field 0
@@ -179,14 +190,17 @@ __device__ __forceinline__ HitF closest_hit_umma(UmmaCtx& ux, const SceneDev& sc
     tc_wait_st();
     tc_fence_before();
     mbar_arrive(ux.bar_afull);
+    RT_STAMP(5);
 
     // the large spheres (f64, ~100 dependent instructions) while the first chunk's MMAs are in flight
     double t_big = __longlong_as_double(0x7ff0000000000000LL); int i_big = -1, c_big = RT_SELF_NONE;
     if (sc.nb > 0) big_spheres_best(sc.big, sc.big_idx, sc.nb, o, dhat, t_min, self_code, self_n, &t_big, &i_big, &c_big);
 
+    RT_STAMP(6);
     int nc = 0;
     for (int c = 0; c < ux.n_chunks; ++c) {
         mbar_wait(ux.bar_full, ux.full_phase); ux.full_phase ^= 1u;
+        RT_STAMP(10 + c);
         tc_fence_after();
 #pragma unroll
         for (int w0 = 0; w0 < NC / 32; w0 += EW) {
@@ -225,6 +239,7 @@ __device__ __forceinline__ HitF closest_hit_umma(UmmaCtx& ux, const SceneDev& sc
             }
         }
     }
+    RT_STAMP(7);
     const int nmax = __reduce_max_sync(RT_FULL, nc);
     for (int k = 0; k < nmax; ++k) {
         if (k < nc) {
@@ -232,6 +247,7 @@ __device__ __forceinline__ HitF closest_hit_umma(UmmaCtx& ux, const SceneDev& sc
             if (p != self_code) { const float4 s = sc.small[p]; candidate<float, true>(o, dhat, inv_a, t_min, mk(s.x, s.y, s.z), s.w, p, &tb, &pb); }
         }
     }
+    RT_STAMP(8);
     HitF h; h.t = tb; h.idx = pb >= 0 ? sc.small_idx[pb] : -1; h.code = pb;
     // merge with the large spheres: t ascending, then list index descending (sphere.rs:29,31 + mod.rs:61-66), compared in f64 as
     // big_spheres_hit does
