@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(G * 160, 1) render_kernel_umma(const RenderArg
     UmmaCtx ux = umma_setup<G, NC>(smem_umma, a.scene, &tmem_base);
     const unsigned lane = threadIdx.x & 31u;
     if (ux.issuer_warp) {
-        if (lane == 0) umma_issuer<G, NC>(ux);
+        umma_issuer<G, NC>(ux);
     } else {
         const unsigned lt_mask = (1u << lane) - 1u;
         PathState<float> ps; init_path(ps);

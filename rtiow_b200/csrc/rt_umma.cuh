@@ -79,6 +79,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         }
     }
 }
+// one lane of a converged warp (what CUTLASS's elect_one_sync does): lets a warp-uniform loop issue single-thread instructions
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred != 0u;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 // barrier + OR-reduction of a predicate over the barrier's threads
 __device__ __forceinline__ bool named_bar_or(int id, int threads, bool pred)

@@ -122,26 +122,38 @@ __device__ __forceinline__ UmmaCtx umma_setup(unsigned char* smem_raw, const Sce
     return ux;
 }
 
-// The group's MMA issuer: ONE thread.  Returns when the group's ray threads have called umma_group_quit.
+// The group's MMA issuer.  The whole warp runs the loop and one elected lane issues: every value the loop touches is broadcast
+// from lane 0 first, so the compiler keeps addresses, descriptors and counters in UNIFORM registers — tcgen05.mma takes its
+// operands from there, and a loop run by a single lane of a diverged warp pays an ELECT + four R2UR.BROADCAST + two PLOP3 per
+// MMA to get them there (75 instructions per chunk; the issuers were 40 % of the issue slots of the scan phase).
+// Returns when the group's ray threads have called umma_group_quit.
 template <int G, int NC>
 __device__ __forceinline__ void umma_issuer(const UmmaCtx& ux)
 {
     using namespace umma;
+    const uint32_t t_d = __shfl_sync(RT_FULL, ux.t_d, 0), t_a = __shfl_sync(RT_FULL, ux.t_a, 0);
+    const uint32_t bar_afull = __shfl_sync(RT_FULL, ux.bar_afull, 0), bar_full = bar_afull + 8u, bar_empty = bar_afull + 16u;
+    const uint32_t s_hi = __shfl_sync(RT_FULL, ux.s_hi, 0), s_lo = __shfl_sync(RT_FULL, ux.s_lo, 0);
+    const int n_chunks = __shfl_sync(RT_FULL, ux.n_chunks, 0);
     const uint32_t idesc = make_idesc_f16_f32(NC);
+    const uint64_t dh0 = make_smem_desc(s_hi, RT_UMMA_B_LBO, RT_UMMA_B_SBO), dl0 = make_smem_desc(s_lo, RT_UMMA_B_LBO, RT_UMMA_B_SBO);
+    constexpr uint32_t kStep = ((uint32_t)(NC / 8) * RT_UMMA_B_SBO) >> 4;     // descriptor start-address units (16 bytes) per chunk
     uint32_t a_phase = 0, e_phase = 0; bool used = false;
     for (;;) {
-        mbar_wait(ux.bar_afull, a_phase); a_phase ^= 1u;                  // all 128 feature rows are in TMEM — or the group is done
+        mbar_wait(bar_afull, a_phase); a_phase ^= 1u;                     // all 128 feature rows are in TMEM — or the group is done
         if (*ux.quit) break;
         tc_fence_after();
-        for (int c = 0; c < ux.n_chunks; ++c) {
-            if (used) { mbar_wait(ux.bar_empty, e_phase); e_phase ^= 1u; tc_fence_after(); }     // the previous chunk's D has been read
+        for (int c = 0; c < n_chunks; ++c) {
+            if (used) { mbar_wait(bar_empty, e_phase); e_phase ^= 1u; tc_fence_after(); }         // the previous chunk's D has been read
             used = true;
-            const uint32_t off = (uint32_t)(c * (NC / 8)) * RT_UMMA_B_SBO;
-            const uint64_t dh = make_smem_desc(ux.s_hi + off, RT_UMMA_B_LBO, RT_UMMA_B_SBO), dl = make_smem_desc(ux.s_lo + off, RT_UMMA_B_LBO, RT_UMMA_B_SBO);
-            mma_f16_ts(ux.t_d, ux.t_a, dh, idesc, 0u);                    // hi . hi
-            mma_f16_ts(ux.t_d, ux.t_a, dl, idesc, 1u);                    // hi . lo
-            mma_f16_ts(ux.t_d, ux.t_a + 8u, dh, idesc, 1u);               // lo . hi
-            tc_commit(ux.bar_full);
+            const uint64_t dh = dh0 + (uint64_t)(kStep * (uint32_t)c), dl = dl0 + (uint64_t)(kStep * (uint32_t)c);
+            if (elect_one()) {
+                mma_f16_ts(t_d, t_a, dh, idesc, 0u);                      // hi . hi
+                mma_f16_ts(t_d, t_a, dl, idesc, 1u);                      // hi . lo
+                mma_f16_ts(t_d, t_a + 8u, dh, idesc, 1u);                 // lo . hi
+                tc_commit(bar_full);
+            }
+            __syncwarp();
         }
     }
 }

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(G * 160, 1) hitlist_kernel_umma(SceneDev sc, i
     uint32_t tmem_base;
     UmmaCtx ux = umma_setup<G, NC>(smem_umma, sc, &tmem_base);
     if (ux.issuer_warp) {
-        if ((threadIdx.x & 31) == 0) umma_issuer<G, NC>(ux);
+        umma_issuer<G, NC>(ux);
     } else {
         const int64_t i = (int64_t)blockIdx.x * (G * 128) + threadIdx.x;
         const bool live = i < n;
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(G * 160, 1) ray_color_kernel_umma(SceneDev sc,
     uint32_t tmem_base;
     UmmaCtx ux = umma_setup<G, NC>(smem_umma, sc, &tmem_base);
     if (ux.issuer_warp) {
-        if ((threadIdx.x & 31) == 0) umma_issuer<G, NC>(ux);
+        umma_issuer<G, NC>(ux);
     } else {
         const int64_t i = (int64_t)blockIdx.x * (G * 128) + threadIdx.x;
         bool active = i < n && max_depth > 0;
