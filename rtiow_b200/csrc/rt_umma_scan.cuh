@@ -119,6 +119,11 @@ __device__ __forceinline__ UmmaCtx umma_setup(unsigned char* smem_raw, const Sce
     ux.n_chunks = sc.u_npad / NC;
     ux.quit = quit + ux.group;
     ux.cand = reinterpret_cast<uint16_t*>(smem_raw) + (ux.issuer_warp ? 0 : tid);
+    // every one of these is the same in all lanes of a warp; broadcasting them from lane 0 tells the compiler so, and it keeps
+    // TMEM addresses and barrier addresses in uniform registers (LDTM / STTM / SYNCS take them from there)
+    ux.t_d = __shfl_sync(RT_FULL, ux.t_d, 0); ux.t_a = __shfl_sync(RT_FULL, ux.t_a, 0); ux.lane_base = __shfl_sync(RT_FULL, ux.lane_base, 0);
+    ux.bar_afull = __shfl_sync(RT_FULL, ux.bar_afull, 0); ux.bar_full = ux.bar_afull + 8; ux.bar_empty = ux.bar_afull + 16;
+    ux.n_chunks = __shfl_sync(RT_FULL, ux.n_chunks, 0);
     return ux;
 }
 
