@@ -78,6 +78,7 @@ struct DeviceState {
     // scene
     DevBuf<float> table; DevBuf<float4> small; DevBuf<int> small_idx; DevBuf<double4> big; DevBuf<int> big_idx;
     DevBuf<float4> sph; DevBuf<double4> sphd; DevBuf<float4> mat; DevBuf<double4> matd; DevBuf<uint8_t> kind;
+    DevBuf<float4> bigf;                               // large spheres, f32 fast path (rt_scene.cuh big_spheres_f32)
     DevBuf<unsigned char> ubimg;                       // tensor-core filter: the spheres' fp16 hi/lo feature image (rt_umma.cuh)
     SceneDev scene{};
     bool has_scene = false;
@@ -316,7 +317,7 @@ extern "C" void rtiow_ctx_destroy(rtiow_ctx* c)
         cudaSetDevice(d.device);
         if (d.stream) cudaStreamSynchronize(d.stream);
         d.table.release(); d.small.release(); d.small_idx.release(); d.big.release(); d.big_idx.release();
-        d.sph.release(); d.sphd.release(); d.mat.release(); d.matd.release(); d.kind.release(); d.ubimg.release();
+        d.sph.release(); d.sphd.release(); d.mat.release(); d.matd.release(); d.kind.release(); d.ubimg.release(); d.bigf.release();
         d.accum.release(); d.counters.release(); d.tiles.release(); d.gathered.release(); d.frame.release();
         d.flush.release(); d.probe.release();
         if (d.pinned) cudaFreeHost(d.pinned);
@@ -396,6 +397,18 @@ extern "C" int rtiow_scene_upload(rtiow_ctx* c, const rtiow_spheres* s, const rt
     }
     for (int k = 0; k < 4; ++k) table[(size_t)np * 4 + 12 + k] = 1e30f;        // the look-ahead record: never hit, never used
     std::vector<double4> big(nb); for (int b = 0; b < nb; ++b) big[b] = sphd[big_ids[b]];
+    // f32 fast path of the large spheres: centre as hi + lo floats, K = |c|^2 - r^2 (from f64) as hi + lo; only offered when the
+    // radius is a float and the centre's lo part is one too (anything else keeps the f64 routine for every ray)
+    std::vector<float4> bigf(3 * (size_t)nb); bool bigf_ok = nb > 0;
+    for (int b = 0; b < nb; ++b) {
+        const double4 v = big[b];
+        const float hx = (float)v.x, hy = (float)v.y, hz = (float)v.z, r = (float)v.w;
+        const float lx = (float)(v.x - hx), ly = (float)(v.y - hy), lz = (float)(v.z - hz);
+        const double K = v.x * v.x + v.y * v.y + v.z * v.z - v.w * v.w;
+        const float Kh = (float)K, Kl = (float)(K - (double)Kh);
+        bigf_ok = bigf_ok && (double)r == v.w && (double)hx + (double)lx == v.x && (double)hy + (double)ly == v.y && (double)hz + (double)lz == v.z && std::isfinite(Kh);
+        bigf[3 * b] = make_float4(hx, hy, hz, r); bigf[3 * b + 1] = make_float4(lx, ly, lz, Kh); bigf[3 * b + 2] = make_float4(Kl, 0.f, 0.f, 0.f);
+    }
     // Tensor-core filter (rt_umma.cuh): per small sphere the 11 features of the bilinear discriminant, scaled by powers of
     // two chosen from the bounding radius, split hi/lo in fp16, in the canonical K-major layout.  S_0 carries the slack that
     // bounds the 3-product split and the fp32 accumulation (tools/probe_umma_filter.cu measures 1.15e-6 R^2; 1.5625e-5 R^2 here).
@@ -438,20 +451,20 @@ extern "C" int rtiow_scene_upload(rtiow_ctx* c, const rtiow_spheres* s, const rt
     for (auto& d : c->dev) {
         CU(cudaSetDevice(d.device));
         CU(d.table.resize(table.size())); CU(d.small.resize(np)); CU(d.small_idx.resize(np)); CU(d.big.resize(nb)); CU(d.big_idx.resize(nb));
-        CU(d.sph.resize(n)); CU(d.sphd.resize(n)); CU(d.mat.resize(n)); CU(d.matd.resize(n)); CU(d.kind.resize(n)); CU(d.ubimg.resize(ubimg.size()));
+        CU(d.sph.resize(n)); CU(d.sphd.resize(n)); CU(d.mat.resize(n)); CU(d.matd.resize(n)); CU(d.kind.resize(n)); CU(d.ubimg.resize(ubimg.size())); CU(d.bigf.resize(bigf.size()));
         size_t bytes = 0;
 #define UP(dst, src, cnt, type) do { if ((cnt) > 0) { CU(cudaMemcpyAsync(dst.p, src.data(), (size_t)(cnt) * sizeof(type), cudaMemcpyHostToDevice, d.stream)); bytes += (size_t)(cnt) * sizeof(type); } } while (0)
         UP(d.table, table, table.size(), float); UP(d.small, small, np, float4); UP(d.small_idx, small_idx, np, int);
         UP(d.big, big, nb, double4); UP(d.big_idx, big_ids, nb, int);
         UP(d.sph, sph, n, float4); UP(d.sphd, sphd, n, double4); UP(d.mat, mat, n, float4); UP(d.matd, matd, n, double4); UP(d.kind, kind, n, uint8_t);
-        UP(d.ubimg, ubimg, ubimg.size(), unsigned char);
+        UP(d.ubimg, ubimg, ubimg.size(), unsigned char); UP(d.bigf, bigf, bigf.size(), float4);
 #undef UP
         CU(cudaStreamSynchronize(d.stream));
         d.scene.table = d.table.p; d.scene.small = d.small.p; d.scene.small_idx = d.small_idx.p; d.scene.np = np; d.scene.n_rec = (ns + 3) / 4;
         d.scene.filter_R2 = R2f; d.scene.filter_sigma = (float)(16.0 * 5.9604644775390625e-08 * std::max(rmax, 1e-3));
         d.scene.big = d.big.p; d.scene.big_idx = d.big_idx.p; d.scene.nb = nb;
         d.scene.sph = d.sph.p; d.scene.sphd = d.sphd.p; d.scene.mat = d.mat.p; d.scene.matd = d.matd.p; d.scene.kind = d.kind.p; d.scene.n = n;
-        d.scene.u_bimg = d.ubimg.p; d.scene.u_npad = u_npad; d.scene.u_sc = u_sc;
+        d.scene.u_bimg = d.ubimg.p; d.scene.u_npad = u_npad; d.scene.u_sc = u_sc; d.scene.bigf = bigf_ok ? d.bigf.p : nullptr;
         d.has_scene = true;
         c->scene_bytes = bytes;
     }

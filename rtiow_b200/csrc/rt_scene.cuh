@@ -31,6 +31,7 @@ struct SceneDev {
     const double4* big;
     const int* big_idx;
     int nb;
+    const float4* bigf;     // the same spheres for the f32 fast path: 3 float4 each: (c_hi, r), (c_lo, K_hi), (K_lo, |c|_1, 0, 0), K = |c|^2 - r^2
     const float4* sph;
     const double4* sphd;
     const float4* mat;
@@ -310,6 +311,63 @@ __device__ __noinline__ void big_spheres_best(const double4* __restrict__ big, c
     *t_out = tbd; *idx_out = ib; *code_out = code;
 }
 
+// The large spheres in f32, for the tensor-core scan.  `half_b^2 - a c` (sphere.rs:24) cancels in f32 for a sphere of radius 1000
+// because c = |o - c|^2 - r^2 is formed from two numbers of size 10^6.  Expanded around the COORDINATE origin instead,
+//     C = |o|^2 - 2 o.c + K ,   K = |c|^2 - r^2  (per sphere, from f64, carried as hi + lo)
+// has terms of the size of the result whenever the origin is near the scene and outside the sphere (the ground: K = 0,
+// C = |o|^2 + 2000 o_y, all positive), and the roots follow without the second cancellation (tca - sqrt) as
+//     q = hb + copysign(sqrt(hb^2 - a C), hb) ,  { q / a , C / q } ,   hb = (c - o).d   (c as hi + lo).
+// A lane whose C does cancel (sum of |terms| > 16 |C|: origins far from the coordinate origin yet close to the surface) reports
+// need64 and takes the f64 routine instead; so does every lane when a sphere's data is not exactly representable.
+// ~35 FP32 instructions instead of ~45 FP64 ones on a pipe that B200 runs at 1/32 of the FP32 rate: 2000 -> 300 cycles per ray.
+__device__ __forceinline__ void big_spheres_f32(const float4* __restrict__ bigf, const int* __restrict__ big_idx, int nb, V3<float> o, V3<float> dhat,
+                                                float t_min, int self_code, V3<float> self_n, float* t_out, int* idx_out, int* code_out, bool* need64)
+{
+    const float a = length_squared(dhat), inv_a = 2.0f - a;
+    const float oo = length_squared(o), od = dot(o, dhat);
+    float tb = __int_as_float(0x7f800000); int ib = -1, code = RT_SELF_NONE; bool bad = false;
+    for (int b = 0; b < nb; ++b) {
+        const float4 q0 = bigf[3 * b], q1 = bigf[3 * b + 1], q2 = bigf[3 * b + 2];
+        const int idx = big_idx[b];
+        float t;
+        if (self_code == -2 - b) {
+            // the sphere the ray starts on: roots {0, 2 tca}, origin taken ON the surface (candidate_self)
+            t = -2.0f * fabsf(q0.w) * dot(self_n, dhat) * inv_a;
+            if (!(t >= t_min)) continue;
+        } else {
+            const V3<float> ch = mk(q0.x, q0.y, q0.z), cl = mk(q1.x, q1.y, q1.z);
+            const float P = dot(o, ch) + dot(o, cl);
+            const float C = (oo - 2.0f * P + q1.w) + q2.x;
+            bad |= (oo + 2.0f * fabsf(P) + fabsf(q1.w)) > 16.0f * fabsf(C);
+            const float hb = (dot(ch, dhat) - od) + dot(cl, dhat);
+            const float disc = hb * hb - a * C;
+            if (disc < 0.0f) continue;                                    // sphere.rs:25
+            const float sq = sqrtf(disc);
+            const float qq = hb + copysignf(sq, hb);
+            const float r0 = qq * inv_a, r1 = C / qq;                      // the two roots (qq == 0 only when hb == C == 0: origin on the surface, tangent)
+            const float t1 = fminf(r0, r1), t2 = fmaxf(r0, r1);
+            t = t1;                                                        // sphere.rs:28
+            if (!(t >= t_min)) { t = t2; if (!(t >= t_min)) continue; }   // sphere.rs:29-33 with t_max = +inf
+        }
+        if (t < tb || (t == tb && idx > ib)) { tb = t; ib = idx; code = -2 - b; }
+    }
+    *t_out = tb; *idx_out = ib; *code_out = code; *need64 = bad;
+}
+
+// The FP32 scan's call: the f32 form, or f64 for the lanes / scenes it does not cover, merged into the closest small-sphere hit
+// by (t ascending, list index descending) — sphere.rs:29,31 + mod.rs:61-66.  Not inlined: once per ray, and kept out of the
+// scan's register allocation (as big_spheres_hit was).
+__device__ __noinline__ HitF big_spheres_merge(const float4* __restrict__ bigf, const double4* __restrict__ big, const int* __restrict__ big_idx, int nb,
+                                               V3<float> o, V3<float> dhat, float t_min, int self_code, V3<float> self_n, HitF h)
+{
+    bool need64 = bigf == nullptr;
+    float tf = __int_as_float(0x7f800000); int ib = -1, cb = RT_SELF_NONE;
+    if (!need64) big_spheres_f32(bigf, big_idx, nb, o, dhat, t_min, self_code, self_n, &tf, &ib, &cb, &need64);
+    if (need64) return big_spheres_hit(big, big_idx, nb, o, dhat, t_min, self_code, self_n, h);
+    if (ib >= 0 && (tf < h.t || (tf == h.t && ib > h.idx))) { h.t = tf; h.idx = ib; h.code = cb; }
+    return h;
+}
+
 // Closest hit of one ray against the whole scene: HittableList::hit (mod.rs:56-69).
 // float: packed filter over the small spheres + f64 test of the big ones; all lanes of the warp
 // must call together.  self_code / self_n identify the sphere the ray starts on (RT_SELF_NONE for
@@ -323,7 +381,7 @@ __device__ __forceinline__ HitF closest_hit(const SceneDev& sc, const float* tab
     int pb = -1;
     scan_small<kSmem>(table, sc.n_rec, sc.filter_R2, sc.filter_sigma, sc.small, o, dhat, inv_a, t_min, self_code, self_n, cand, cand_stride, &tb, &pb);
     HitF h; h.t = tb; h.idx = pb >= 0 ? sc.small_idx[pb] : -1; h.code = pb;
-    if (sc.nb > 0) h = big_spheres_hit(sc.big, sc.big_idx, sc.nb, o, dhat, t_min, self_code, self_n, h);
+    if (sc.nb > 0) h = big_spheres_merge(sc.bigf, sc.big, sc.big_idx, sc.nb, o, dhat, t_min, self_code, self_n, h);
     return h;
 }
 

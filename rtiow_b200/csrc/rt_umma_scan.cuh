@@ -209,9 +209,14 @@ __device__ __forceinline__ HitF closest_hit_umma(UmmaCtx& ux, const SceneDev& sc
     mbar_arrive(ux.bar_afull);
     RT_STAMP(5);
 
-    // the large spheres (f64, ~100 dependent instructions) while the first chunk's MMAs are in flight
+    // the large spheres while the first chunk's MMAs are in flight: f32 through the cancellation-free form (big_spheres_f32);
+    // lanes whose origin defeats it, and scenes whose large spheres are not f32-representable, take the f64 routine
     double t_big = __longlong_as_double(0x7ff0000000000000LL); int i_big = -1, c_big = RT_SELF_NONE;
-    if (sc.nb > 0) big_spheres_best(sc.big, sc.big_idx, sc.nb, o, dhat, t_min, self_code, self_n, &t_big, &i_big, &c_big);
+    if (sc.nb > 0) {
+        bool need64 = sc.bigf == nullptr;
+        if (!need64) { float tf; big_spheres_f32(sc.bigf, sc.big_idx, sc.nb, o, dhat, t_min, self_code, self_n, &tf, &i_big, &c_big, &need64); t_big = (double)tf; }
+        if (need64) big_spheres_best(sc.big, sc.big_idx, sc.nb, o, dhat, t_min, self_code, self_n, &t_big, &i_big, &c_big);
+    }
 
     RT_STAMP(6);
     int nc = 0;
