@@ -66,18 +66,34 @@ __device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok;
 }
-// Bounded wait: a protocol error must end in a trap (a loud launch failure), never in a hung GPU.  The clock is only
-// consulted every 4096 failed attempts.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+// Bounded wait (the MMA issuers): a protocol error must end in a trap (a loud launch failure), never in a hung GPU.  Every
+// deadlock of the scan's protocol leaves an issuer waiting for its ray threads, so the guard lives here only; the clock is
+// consulted every 4096 failed attempts.  `backoff_ns` > 0 sleeps between attempts: the suspended try_wait is woken by EVERY
+// barrier event on the SM, and each wake-up that finds the phase unchanged costs issue slots the ray warps need (ncu: the
+// issuers' waits for their groups' per-ray phase were 12 % of all issue cycles).
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t backoff_ns = 0)
 {
     uint32_t spins = 0; long long t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
+        if (backoff_ns) __nanosleep(backoff_ns);
         if ((++spins & 4095u) == 0u) {
             const long long now = clock64();
             if (t0 == 0) t0 = now;
             else if (now - t0 > 8000000000ll) __trap();       // ~4 s at 1.9 GHz
         }
     }
+}
+// Unguarded wait (the ray threads' wait for their issuer's commit): the bare try_wait loop, four instructions per attempt.
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}"
+        ::"r"(bar), "r"(parity), "r"(1000000u) : "memory");
 }
 // one lane of a converged warp (what CUTLASS's elect_one_sync does): lets a warp-uniform loop issue single-thread instructions
 __device__ __forceinline__ bool elect_one()
