@@ -184,10 +184,27 @@ __device__ __forceinline__ void umma_teardown(uint32_t tmem_base)
 
 // Closest hit of one ray against the whole scene — the tensor-core twin of closest_hit<kSmem> (rt_scene.cuh); every one of
 // the group's 128 ray threads must call together (lanes without a ray pass anything: their result is ignored).
+// `has_ray`: this lane carries a ray.  A warp without any (the end of a frame: the queue is empty and its paths are done, while
+// a neighbour's 50-bounce path keeps the group scanning) only keeps the group's barriers moving — no feature rows, no TMEM
+// loads, no sign collection — so that the warps that still work get the SM to themselves and the frame's tail gets shorter.
 template <int G, int NC, int EW = NC / 32>
-__device__ __forceinline__ HitF closest_hit_umma(UmmaCtx& ux, const SceneDev& sc, V3<float> o, V3<float> dhat, float t_min, int self_code, V3<float> self_n)
+__device__ __forceinline__ HitF closest_hit_umma(UmmaCtx& ux, const SceneDev& sc, V3<float> o, V3<float> dhat, float t_min, int self_code, V3<float> self_n,
+                                                 bool has_ray = true)
 {
     using namespace umma;
+    if (!__any_sync(RT_FULL, has_ray)) {
+        tc_fence_before();
+        mbar_arrive(ux.bar_afull);                                         // (the rows this warp left in A belong to nobody: their D rows are never read)
+        for (int c = 0; c < ux.n_chunks; ++c) {
+            mbar_wait_spin(ux.bar_full, ux.full_phase); ux.full_phase ^= 1u;
+            tc_fence_after();
+            tc_fence_before();
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) mbar_arrive(ux.bar_empty);
+        }
+        HitF none; none.t = __int_as_float(0x7f800000); none.idx = -1; none.code = RT_SELF_NONE;
+        return none;
+    }
     static_assert(EW >= 1 && (NC / 32) % EW == 0, "EW = 32-sphere words loaded from TMEM at a time");
     constexpr int kStride = UmmaShape<G, NC>::kRayThreads;
     const float inv_a = 2.0f - length_squared(dhat);           // 1/a for a = 1 + e, |e| < 1e-6
