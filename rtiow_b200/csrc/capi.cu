@@ -422,15 +422,20 @@ extern "C" int rtiow_scene_upload(rtiow_ctx* c, const rtiow_spheres* s, const rt
         const double slack = 1.5625e-5 * R * R;
         double mean_r2 = 0; for (int id : small_ids) mean_r2 += (double)sph[id].w * sph[id].w;
         mean_r2 = ns ? mean_r2 / ns : 0.0;
-        if (ns > 0 && npad < 65536 && Shape::smem_bytes(npad) <= 227 * 1024 && Rp <= 8192.0 && slack <= mean_r2) {
+        // fp16 accumulator (RT_UMMA_D16): |D| <= 4 R^2 for a line that meets the bounding sphere; it must stay finite in fp16
+        const bool d_fits = !RT_UMMA_D16 || 4.0 * R * R < 60000.0;
+        if (ns > 0 && npad < 65536 && Shape::smem_bytes(npad) <= 227 * 1024 && Rp <= 8192.0 && slack <= mean_r2 && d_fits) {
             u_npad = npad;
             u_sc = umma::FeatScale{ (float)Rp, 1.0f, (float)(Rp * 0.5), (float)(1.0 / Rp) };
             const size_t blk = RT_UMMA_B_BLOCK_BYTES(npad);
             ubimg.assign(2 * blk, 0);
+            // sphere j of `small` sits in column col(j) of the image: with the fp16 accumulator the columns of a 32-sphere word are
+            // permuted so that the packed sign collection (umma::sign_word16) returns bit 31 - k for sphere k, as the funnel shifts do
             auto put = [&](int j, int k, double val) {
                 const float x = (float)val; const __half h = __float2half_rn(x); const __half l = __float2half_rn(x - __half2float(h));
-                memcpy(&ubimg[umma::b_offset(j, k)], &h, 2);
-                memcpy(&ubimg[blk + umma::b_offset(j, k)], &l, 2);
+                const uint32_t col = RT_UMMA_D16 ? (((uint32_t)j & ~31u) | umma::d16_column((uint32_t)j & 31u)) : (uint32_t)j;
+                memcpy(&ubimg[umma::b_offset(col, k)], &h, 2);
+                memcpy(&ubimg[blk + umma::b_offset(col, k)], &l, 2);
             };
             for (int j = 0; j < npad; ++j) {
                 if (j < ns) {                     // position j of `small` (list order); the f32 sphere the precise test sees

@@ -140,6 +140,14 @@ __host__ __device__ constexpr uint32_t make_idesc_f16_f32(int n)
            | ((uint32_t)(n >> 3) << 17)    // n_dim
            | ((uint32_t)(128 >> 4) << 24); // m_dim
 }
+// the same with an fp16 accumulator (c_format F16).  Only the SIGN of D is used; rounding the final sum to fp16 keeps it, and the
+// tensor core still adds the 16 products and C at fp32 precision inside one instruction (tools/probe_umma_filter.cu, F_D16:
+// the error where |D| is small is 8.6e-5 against 6.9e-5 with an fp32 D, the same candidates).  What it buys: D comes back as
+// packed halves — 32 spheres in 16 registers — whose sign bits can be collected four per instruction (sign_word16).
+__host__ __device__ constexpr uint32_t make_idesc_f16_f16(int n)
+{
+    return (0u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
 // shared-memory matrix descriptor, no swizzle, K-major: core matrix = 8 rows x 16 bytes stored as 128 contiguous bytes;
 // lbo = byte distance between the two core matrices along K, sbo = byte distance between 8-row groups along N
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo)
@@ -159,6 +167,36 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
           "=r"(v[31])
         : "r"(taddr) : "memory");
 }
+// one 32-sphere word of an fp16 D: 32 consecutive columns, two per register (column 2i in the low half of register i)
+__device__ __forceinline__ void tmem_ld16p(uint32_t taddr, uint32_t (&v)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.pack::16b.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr) : "memory");
+}
+// Sign bits of 32 packed halves, FOUR per instruction: PRMT with sign replication (selector nibble | 8) turns the sign bytes of
+// two registers into four bytes of 0x00 / 0xff, and a LOP3 bit-select tree interleaves eight such words: 8 PRMT + 7 LOP3 per
+// 32 spheres where one SHF per sphere was 28 % of the render kernel's issue cycles (all on the half-rate ALU pipe).
+// Bit 8 b + j of the result = sign of column 4 j + b; d16_column() is the inverse, used when the B image is laid out.
+__device__ __forceinline__ uint32_t sign_bytes(uint32_t a, uint32_t b)
+{
+    uint32_t d; asm("prmt.b32 %0, %1, %2, 0xfdb9;" : "=r"(d) : "r"(a), "r"(b)); return d;
+}
+__device__ __forceinline__ uint32_t sign_word16(const uint32_t (&v)[16])
+{
+    uint32_t d[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d[j] = sign_bytes(v[2 * j], v[2 * j + 1]);
+    const uint32_t x0 = (d[0] & 0x55555555u) | (d[1] & 0xaaaaaaaau), x1 = (d[2] & 0x55555555u) | (d[3] & 0xaaaaaaaau);
+    const uint32_t x2 = (d[4] & 0x55555555u) | (d[5] & 0xaaaaaaaau), x3 = (d[6] & 0x55555555u) | (d[7] & 0xaaaaaaaau);
+    const uint32_t y0 = (x0 & 0x33333333u) | (x1 & 0xccccccccu), y1 = (x2 & 0x33333333u) | (x3 & 0xccccccccu);
+    return (y0 & 0x0f0f0f0fu) | (y1 & 0xf0f0f0f0u);
+}
+// column (within its 32-sphere word) that holds sphere k of the word, so that sign_word16's bit 31 - k belongs to sphere k — the
+// bit order the FP32 filter's funnel shifts produce, and with it the same candidate order
+__host__ __device__ constexpr uint32_t d16_column(uint32_t k) { return 4u * ((31u - k) & 7u) + ((31u - k) >> 3); }
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
 {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"

@@ -35,6 +35,9 @@ namespace rt {
 #ifndef RT_UMMA_EW
 #define RT_UMMA_EW 1                          // 32-sphere words fetched from TMEM at a time (registers: 32 per word)
 #endif
+#ifndef RT_UMMA_D16
+#define RT_UMMA_D16 1                         // fp16 accumulator + packed sign collection (rt_umma.cuh, sign_word16); 0: fp32 D, one SHF per sphere
+#endif
 #define RT_UMMA_MIN_SMEM (120 * 1024)        // > half an SM's shared memory: one CTA per SM (each CTA allocates all of TMEM)
 
 template <int G, int NC> struct UmmaShape {
@@ -143,7 +146,7 @@ __device__ __forceinline__ void umma_issuer(const UmmaCtx& ux)
     const uint32_t bar_afull = __shfl_sync(RT_FULL, ux.bar_afull, 0), bar_full = bar_afull + 8u, bar_empty = bar_afull + 16u;
     const uint32_t s_hi = __shfl_sync(RT_FULL, ux.s_hi, 0), s_lo = __shfl_sync(RT_FULL, ux.s_lo, 0);
     const int n_chunks = __shfl_sync(RT_FULL, ux.n_chunks, 0);
-    const uint32_t idesc = make_idesc_f16_f32(NC);
+    const uint32_t idesc = RT_UMMA_D16 ? make_idesc_f16_f16(NC) : make_idesc_f16_f32(NC);
     const uint64_t dh0 = make_smem_desc(s_hi, RT_UMMA_B_LBO, RT_UMMA_B_SBO), dl0 = make_smem_desc(s_lo, RT_UMMA_B_LBO, RT_UMMA_B_SBO);
     constexpr uint32_t kStep = ((uint32_t)(NC / 8) * RT_UMMA_B_SBO) >> 4;     // descriptor start-address units (16 bytes) per chunk
     uint32_t a_phase = 0, e_phase = 0; bool used = false;
@@ -156,9 +159,15 @@ __device__ __forceinline__ void umma_issuer(const UmmaCtx& ux)
             used = true;
             const uint64_t dh = dh0 + (uint64_t)(kStep * (uint32_t)c), dl = dl0 + (uint64_t)(kStep * (uint32_t)c);
             if (elect_one()) {
+#if RT_UMMA_D16
+                mma_f16_ts(t_d, t_a, dl, idesc, 0u);                      // hi . lo   the small cross terms first: the fp16 rounding of the
+                mma_f16_ts(t_d, t_a + 8u, dh, idesc, 1u);                 // lo . hi   intermediate D costs ~2^-12 of THEM;
+                mma_f16_ts(t_d, t_a, dh, idesc, 1u);                      // hi . hi   the last sum is rounded once and keeps its sign
+#else
                 mma_f16_ts(t_d, t_a, dh, idesc, 0u);                      // hi . hi
                 mma_f16_ts(t_d, t_a, dl, idesc, 1u);                      // hi . lo
                 mma_f16_ts(t_d, t_a + 8u, dh, idesc, 1u);                 // lo . hi
+#endif
                 tc_commit(bar_full);
             }
             __syncwarp();
@@ -244,6 +253,26 @@ __device__ __forceinline__ HitF closest_hit_umma(UmmaCtx& ux, const SceneDev& sc
         mbar_wait_spin(ux.bar_full, ux.full_phase); ux.full_phase ^= 1u;
         RT_STAMP(10 + c);
         tc_fence_after();
+#if RT_UMMA_D16
+        uint32_t v[NC / 32][16];
+#pragma unroll
+        for (int w = 0; w < NC / 32; ++w) tmem_ld16p(ux.t_d + ux.lane_base + 32u * w, v[w]);
+        tc_wait_ld();
+        tc_fence_before();                                                     // hand D back to the issuer, whose next MMAs then
+        __syncwarp();                                                          // overlap the sign collection
+        if ((threadIdx.x & 31) == 0) mbar_arrive(ux.bar_empty);
+#pragma unroll
+        for (int w = 0; w < NC / 32; ++w) {
+            unsigned pass = ~sign_word16(v[w]);                                // bit (31-k) set: sphere k of the word passed the filter
+            while (pass) {
+                const int k = __clz(pass);
+                pass &= ~(0x80000000u >> k);
+                const int p = c * NC + w * 32 + k;
+                if (nc < RT_CAND_CAP) { ux.cand[nc * kStride] = (uint16_t)p; ++nc; }
+                else if (p != self_code) { const float4 s = sc.small[p]; candidate<float, true>(o, dhat, inv_a, t_min, mk(s.x, s.y, s.z), s.w, p, &tb, &pb); }
+            }
+        }
+#else
 #pragma unroll
         for (int w0 = 0; w0 < NC / 32; w0 += EW) {
             uint32_t v[EW][32];
@@ -280,6 +309,7 @@ __device__ __forceinline__ HitF closest_hit_umma(UmmaCtx& ux, const SceneDev& sc
                 }
             }
         }
+#endif
     }
     RT_STAMP(7);
     // survivors through the precise test, the warp in lock step, TWO per round: the test is one dependent chain (load, ~25 FP

@@ -39,7 +39,41 @@ struct ProbeArgs {
     long long* trace;            // F_TRACE: clock64 stamps of block 0, group 0, warp 0, lane 0 during scan `iters - 1`
 };
 
-enum { F_MMA = 1, F_SIGN = 2, F_DUMP = 4, F_SWAP = 8, F_NOLD = 16, F_TRACE = 32, F_SIGN3 = 64 };
+enum { F_MMA = 1, F_SIGN = 2, F_DUMP = 4, F_SWAP = 8, F_NOLD = 16, F_TRACE = 32, F_SIGN3 = 64, F_D16 = 128 };
+
+// F_D16: the accumulator in fp16 (idesc c_format = F16).  Only the SIGN of D is used, and rounding the final sum to fp16 keeps
+// it; the cross terms go first (they are small: fp16 rounding of the intermediate D costs ~1e-4) and hi.hi last.  D then comes
+// back as packed halves (tcgen05.ld ... .pack::16b: 32 spheres in 16 registers) and the sign bits are collected FOUR per
+// instruction: PRMT with sign replication turns two registers into four sign bytes, a LOP3 bit-select tree interleaves eight
+// such words into one 32-sphere mask: 8 PRMT + 7 LOP3 per word instead of 32 SHF.
+__host__ __device__ constexpr uint32_t make_idesc_f16_f16(int n)
+{
+    return (0u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld16p(uint32_t taddr, uint32_t (&v)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.pack::16b.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr) : "memory");
+}
+// bytes 1 and 3 of a, bytes 1 and 3 of b, each replaced by eight copies of its sign bit
+__device__ __forceinline__ uint32_t sign_bytes(uint32_t a, uint32_t b)
+{
+    uint32_t d; asm("prmt.b32 %0, %1, %2, 0xfdb9;" : "=r"(d) : "r"(a), "r"(b)); return d;
+}
+// 16 packed registers (32 halves) -> 32 sign bits: bit 8 b + j = sign of half (4 j + b)
+__device__ __forceinline__ uint32_t sign_word16(const uint32_t (&v)[16])
+{
+    uint32_t d[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d[j] = sign_bytes(v[2 * j], v[2 * j + 1]);
+    const uint32_t x0 = (d[0] & 0x55555555u) | (d[1] & 0xaaaaaaaau), x1 = (d[2] & 0x55555555u) | (d[3] & 0xaaaaaaaau);
+    const uint32_t x2 = (d[4] & 0x55555555u) | (d[5] & 0xaaaaaaaau), x3 = (d[6] & 0x55555555u) | (d[7] & 0xaaaaaaaau);
+    const uint32_t y0 = (x0 & 0x33333333u) | (x1 & 0xccccccccu), y1 = (x2 & 0x33333333u) | (x3 & 0xccccccccu);
+    return (y0 & 0x0f0f0f0fu) | (y1 & 0xf0f0f0f0u);
+}
 
 template <int G, int NC, int NBUF, int FLAGS>
 __global__ void __launch_bounds__(G * 160, 1) probe_kernel(const ProbeArgs a)
@@ -86,7 +120,7 @@ __global__ void __launch_bounds__(G * 160, 1) probe_kernel(const ProbeArgs a)
 
     if (issuer_warp) {
         if (lane == 0 && (FLAGS & F_MMA)) {
-            const uint32_t idesc = make_idesc_f16_f32(NC);
+            const uint32_t idesc = (FLAGS & F_D16) ? make_idesc_f16_f16(NC) : make_idesc_f16_f32(NC);
             const uint32_t lbo = (FLAGS & F_SWAP) ? RT_UMMA_B_SBO : RT_UMMA_B_LBO, sbo = (FLAGS & F_SWAP) ? RT_UMMA_B_LBO : RT_UMMA_B_SBO;
             const uint32_t s_hi = smem_u32(b_hi), s_lo = smem_u32(b_lo);
             uint32_t a_phase = 0, use_phase = 0, used = 0;
@@ -100,9 +134,15 @@ __global__ void __launch_bounds__(G * 160, 1) probe_kernel(const ProbeArgs a)
                     const uint32_t t_d = col0 + b * NC;
                     const uint32_t off = (uint32_t)(c * (NC / 8)) * 256u;
                     const uint64_t dh = make_smem_desc(s_hi + off, lbo, sbo), dl = make_smem_desc(s_lo + off, lbo, sbo);
-                    mma_f16_ts(t_d, t_ahi, dh, idesc, 0u);
-                    mma_f16_ts(t_d, t_ahi, dl, idesc, 1u);
-                    mma_f16_ts(t_d, t_alo, dh, idesc, 1u);
+                    if (FLAGS & F_D16) {
+                        mma_f16_ts(t_d, t_ahi, dl, idesc, 0u);               // hi . lo
+                        mma_f16_ts(t_d, t_alo, dh, idesc, 1u);               // lo . hi
+                        mma_f16_ts(t_d, t_ahi, dh, idesc, 1u);               // hi . hi last: the final rounding to fp16 keeps the sign
+                    } else {
+                        mma_f16_ts(t_d, t_ahi, dh, idesc, 0u);
+                        mma_f16_ts(t_d, t_ahi, dl, idesc, 1u);
+                        mma_f16_ts(t_d, t_alo, dh, idesc, 1u);
+                    }
                     tc_commit(bar_full0 + 8u * b);
                 }
             }
@@ -140,6 +180,41 @@ __global__ void __launch_bounds__(G * 160, 1) probe_kernel(const ProbeArgs a)
                 STAMP();
                 tc_fence_after();
                 constexpr int NW = NC / 32;
+                if (FLAGS & F_D16) {
+                    uint32_t v[NW][16];
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) tmem_ld16p(col0 + b * NC + lane_base + 32 * w, v[w]);
+                    tc_wait_ld();
+                    STAMP();
+                    if (FLAGS & F_MMA) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(bar_empty0 + 8u * b); }
+                    if ((FLAGS & F_DUMP) && it == 0 && ray < a.dump_rays) {
+#pragma unroll
+                        for (int w = 0; w < NW; ++w)
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) {
+                                const __half2 h = *reinterpret_cast<const __half2*>(&v[w][k]);
+                                a.dump[(size_t)ray * a.npad + c * NC + w * 32 + 2 * k] = __low2float(h);
+                                a.dump[(size_t)ray * a.npad + c * NC + w * 32 + 2 * k + 1] = __high2float(h);
+                            }
+                    }
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) {
+                        if (FLAGS & F_SIGN) {
+                            const unsigned m = sign_word16(v[w]); cand += __popc(~m);
+                            if (FLAGS & F_DUMP) {                             // self-check of the bit order: bit 8 b + j = sign of half 4 j + b
+                                unsigned ref = 0;
+#pragma unroll
+                                for (int h = 0; h < 32; ++h) ref |= ((v[w][h >> 1] >> ((h & 1) ? 31 : 15)) & 1u) << (8 * (h & 3) + (h >> 2));
+                                xr += (m != ref);
+                            } else xr ^= m;
+                        }
+                        else {
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) asm volatile("" ::"r"(v[w][k]));
+                        }
+                    }
+                    continue;
+                }
                 // SIGN3 needs its three words together; otherwise two words (64 registers) are in flight at a time
                 constexpr int SUB = (FLAGS & F_SIGN3) ? 3 : (NW >= 2 ? 2 : 1);
 #pragma unroll
@@ -329,7 +404,7 @@ int main(int argc, char** argv)
         }
     sp.push_back({0, 1, 0, 1}); sp.push_back({-4, 1, 0, 1}); sp.push_back({4, 1, 0, 1});
     const int n_real = (int)sp.size();
-    const int npad = (n_real + 191) / 192 * 192;                   // a multiple of every chunk size tried (32, 64, 96)
+    const int npad = (n_real + 383) / 384 * 384;                   // a multiple of every chunk size tried (32, 64, 96, 128)
     double Rs = 0; for (auto& s : sp) Rs = std::max(Rs, std::sqrt(s.x * s.x + s.y * s.y + s.z * s.z) + s.r);
     const float Rp = std::exp2(std::ceil(std::log2(Rs)));          // power of two >= the bounding radius
     FeatScale sc{Rp, 1.0f, Rp * 0.5f, 1.0f / Rp};
@@ -378,7 +453,7 @@ int main(int argc, char** argv)
 
     ProbeArgs a{};
     unsigned char* d_b; float4 *d_o, *d_d; float* d_dump; unsigned long long* d_out;
-    const int dump_rays = 4 * 128;
+    const int dump_rays = 32 * 128;
     CK(cudaMalloc(&d_b, bimg.size())); CK(cudaMemcpy(d_b, bimg.data(), bimg.size(), cudaMemcpyHostToDevice));
     CK(cudaMalloc(&d_o, n_rays * sizeof(float4))); CK(cudaMemcpy(d_o, ro.data(), n_rays * sizeof(float4), cudaMemcpyHostToDevice));
     CK(cudaMalloc(&d_d, n_rays * sizeof(float4))); CK(cudaMemcpy(d_d, rd.data(), n_rays * sizeof(float4), cudaMemcpyHostToDevice));
@@ -391,17 +466,19 @@ int main(int argc, char** argv)
     const size_t smem_bytes = std::max<size_t>(2 * RT_UMMA_B_BLOCK_BYTES(npad) + 1024, 120 * 1024);
 
     // ---- accuracy: both readings of LBO/SBO --------------------------------------------------------------------------
-    for (int swap = 0; swap < 2; ++swap) {
+    for (int swap = 0; swap < 3; ++swap) {                        // 2: fp16 accumulator (F_D16)
         ProbeArgs c = a; c.iters = 1;
         CK(cudaMemset(d_dump, 0, (size_t)dump_rays * npad * sizeof(float)));
         CK(cudaMemset(d_out, 0, 16));
         auto k0 = probe_kernel<2, 64, 2, F_MMA | F_SIGN | F_DUMP>; auto k1 = probe_kernel<2, 64, 2, F_MMA | F_SIGN | F_DUMP | F_SWAP>;
-        CK(cudaFuncSetAttribute(swap ? k1 : k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-        (swap ? k1 : k0)<<<sms, 320, smem_bytes>>>(c);
+        auto k2 = probe_kernel<2, 64, 2, F_MMA | F_SIGN | F_DUMP | F_D16>;
+        auto kk = swap == 2 ? k2 : swap ? k1 : k0;
+        CK(cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        kk<<<sms, 320, smem_bytes>>>(c);
         CK(cudaDeviceSynchronize());
         std::vector<float> D((size_t)dump_rays * npad);
         CK(cudaMemcpy(D.data(), d_dump, D.size() * sizeof(float), cudaMemcpyDeviceToHost));
-        double max_err = 0, sum_err = 0; long n = 0, false_neg = 0, exact_pos = 0, filt_pos = 0, pad_pos = 0, dead = 0;
+        double max_err = 0, sum_err = 0, max_err_small = 0, max_excess = 0; long n = 0, false_neg = 0, exact_pos = 0, filt_pos = 0, pad_pos = 0, dead = 0;
         for (int r = 0; r < dump_rays; ++r) {
             const double o[3] = {ro[r].x, ro[r].y, ro[r].z}, d[3] = {rd[r].x, rd[r].y, rd[r].z};
             const double aa = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
@@ -423,13 +500,17 @@ int main(int argc, char** argv)
                 if (!live) { if (disc >= 0) ++false_neg; continue; }       // a dead ray must not be able to hit anything
                 const double err = std::fabs((double)got - (disc + slack * aa));
                 max_err = std::max(max_err, err); sum_err += err; ++n;
+                if (std::fabs(disc + slack * aa) < 0.05) max_err_small = std::max(max_err_small, err);          // where the sign is decided
+                max_excess = std::max(max_excess, err - std::fabs(disc + slack * aa) * (1.0 / 1024.0));         // beyond one fp16 rounding of the result
                 if (got >= 0) ++filt_pos;
                 if (disc >= 0 && !(got >= 0)) ++false_neg;
             }
         }
         printf("{\"probe\":\"umma_accuracy\",\"lbo_sbo_swapped\":%d,\"rays\":%d,\"spheres\":%d,\"npad\":%d,\"scale_Rp\":%.1f,\"slack\":%.3e,\"max_abs_err\":%.4e,"
-               "\"mean_abs_err\":%.4e,\"false_negatives\":%ld,\"exact_positive\":%ld,\"filter_positive\":%ld,\"padding_positive\":%ld,\"dead_rays\":%ld}\n",
-               swap, dump_rays, n_real, npad, Rp, slack, max_err, n ? sum_err / n : 0.0, false_neg, exact_pos, filt_pos, pad_pos, dead);
+               "\"mean_abs_err\":%.4e,\"false_negatives\":%ld,\"exact_positive\":%ld,\"filter_positive\":%ld,\"padding_positive\":%ld,\"dead_rays\":%ld,"
+               "\"d_fp16\":%d,\"max_abs_err_where_small\":%.4e,\"max_err_beyond_fp16_rounding\":%.4e,\"mask_mismatches\":%llu}\n",
+               swap == 1, dump_rays, n_real, npad, Rp, slack, max_err, n ? sum_err / n : 0.0, false_neg, exact_pos, filt_pos, pad_pos, dead,
+               swap == 2, max_err_small, max_excess, [&] { unsigned long long o[2]; CK(cudaMemcpy(o, d_out, 16, cudaMemcpyDeviceToHost)); return swap == 2 ? o[1] : 0ull; }());
         fflush(stdout);
     }
 
@@ -456,6 +537,13 @@ int main(int argc, char** argv)
     }
 
     // ---- throughput ----
+    run<6, 64, 1, F_MMA | F_SIGN>("full", a, n_real, smem_bytes, sms);
+    run<6, 64, 1, F_MMA | F_SIGN | F_D16>("full, fp16 D + PRMT/LOP3 signs", a, n_real, smem_bytes, sms);
+    run<4, 64, 1, F_MMA | F_SIGN | F_D16>("full, fp16 D + PRMT/LOP3 signs", a, n_real, smem_bytes, sms);
+    run<3, 64, 2, F_MMA | F_SIGN | F_D16>("full, fp16 D + PRMT/LOP3 signs", a, n_real, smem_bytes, sms);
+    run<3, 128, 1, F_MMA | F_SIGN | F_D16>("full, fp16 D + PRMT/LOP3 signs", a, n_real, smem_bytes, sms);
+    run<4, 64, 1, F_SIGN | F_D16>("ld+sign, fp16 D", a, n_real, smem_bytes, sms);
+    run<4, 64, 1, F_MMA | F_D16>("mma+ld, fp16 D", a, n_real, smem_bytes, sms);
     run<3, 64, 2, F_MMA | F_SIGN>("full", a, n_real, smem_bytes, sms);
     run<2, 96, 2, F_MMA | F_SIGN>("full", a, n_real, smem_bytes, sms);
     run<3, 96, 1, F_MMA | F_SIGN>("full", a, n_real, smem_bytes, sms);
