@@ -431,24 +431,31 @@ extern "C" int rtiow_scene_upload(rtiow_ctx* c, const rtiow_spheres* s, const rt
             ubimg.assign(2 * blk, 0);
             // sphere j of `small` sits in column col(j) of the image: with the fp16 accumulator the columns of a 32-sphere word are
             // permuted so that the packed sign collection (umma::sign_word16) returns bit 31 - k for sphere k, as the funnel shifts do
-            auto put = [&](int j, int k, double val) {
-                const float x = (float)val; const __half h = __float2half_rn(x); const __half l = __float2half_rn(x - __half2float(h));
+            // K slots of the two blocks: umma::b2_feature (block 0 = B1: every hi feature + the hi parts that meet the ray's lo
+            // parts of features 10 and 0..3; block 1 = B2: the lo parts of features 0..9 + the hi parts that meet lo_4..lo_9)
+            auto put_all = [&](int j, const double (&S)[11]) {
                 const uint32_t col = RT_UMMA_D16 ? (((uint32_t)j & ~31u) | umma::d16_column((uint32_t)j & 31u)) : (uint32_t)j;
-                memcpy(&ubimg[umma::b_offset(col, k)], &h, 2);
-                memcpy(&ubimg[blk + umma::b_offset(col, k)], &l, 2);
+                for (int b = 0; b < 2; ++b)
+                    for (int s = 0; s < 16; ++s) {
+                        int feat; bool is_lo; umma::b2_feature(b, s, &feat, &is_lo);
+                        const float x = (float)S[feat]; const __half h = __float2half_rn(x); const __half l = __float2half_rn(x - __half2float(h));
+                        memcpy(&ubimg[b * blk + umma::b_offset(col, s)], is_lo ? &l : &h, 2);
+                    }
             };
             for (int j = 0; j < npad; ++j) {
+                double S[11] = { 0 };
                 if (j < ns) {                     // position j of `small` (list order); the f32 sphere the precise test sees
                     const float4 v = sph[order[j]];
                     const double x = v.x, y = v.y, z = v.z, r = v.w;
-                    put(j, 0, (r * r - (x * x + y * y + z * z) + slack) / u_sc.s0);
-                    put(j, 1, x / u_sc.s1); put(j, 2, y / u_sc.s1); put(j, 3, z / u_sc.s1);
-                    put(j, 4, x * x / u_sc.s4); put(j, 5, y * y / u_sc.s4); put(j, 6, z * z / u_sc.s4);
-                    put(j, 7, x * y / u_sc.s4); put(j, 8, x * z / u_sc.s4); put(j, 9, y * z / u_sc.s4);
+                    S[0] = (r * r - (x * x + y * y + z * z) + slack) / u_sc.s0;
+                    S[1] = x / u_sc.s1; S[2] = y / u_sc.s1; S[3] = z / u_sc.s1;
+                    S[4] = x * x / u_sc.s4; S[5] = y * y / u_sc.s4; S[6] = z * z / u_sc.s4;
+                    S[7] = x * y / u_sc.s4; S[8] = x * z / u_sc.s4; S[9] = y * z / u_sc.s4;
                 } else {
-                    put(j, 0, -4.0 * Rp * Rp / u_sc.s0);              // padding: never passes, whatever the ray
+                    S[0] = -4.0 * Rp * Rp / u_sc.s0;                  // padding: never passes, whatever the ray
                 }
-                put(j, 10, 1.0 / u_sc.s10);
+                S[10] = 1.0 / u_sc.s10;                               // a power of two: no lo part (the two-product form relies on it)
+                put_all(j, S);
             }
         }
     }

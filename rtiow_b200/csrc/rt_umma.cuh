@@ -216,15 +216,14 @@ __host__ __device__ constexpr uint32_t b_offset(uint32_t j, uint32_t k) { return
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) { __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
 
-// The ray's A rows: hi[8] / lo[8] hold 16 fp16 each (features 0..10, then zeros).  (o, dhat): any point of the line and
-// its (nearly) unit direction; `live` false -> the line cannot touch any sphere of the table and every product is < 0.
-// `sigma` >= 0 is a per-ray slack added to the discriminant (it multiplies S_10 = 1).
-__device__ __forceinline__ void ray_features(float ox, float oy, float oz, float dx, float dy, float dz, bool live, float sigma, const FeatScale sc,
-                                             uint32_t (&hi)[8], uint32_t (&lo)[8])
+// The ray's 11 scaled features.  (o, dhat): any point of the line and its (nearly) unit direction; `live` false -> the line
+// cannot touch any sphere of the table and every product is < 0.  `sigma` >= 0 is a per-ray slack added to the discriminant
+// (it multiplies S_10 = 1).
+__device__ __forceinline__ void ray_feature_values(float ox, float oy, float oz, float dx, float dy, float dz, bool live, float sigma, const FeatScale sc,
+                                                   float (&R)[12])
 {
     const float a = dx * dx + dy * dy + dz * dz;
     const float fd = ox * dx + oy * dy + oz * dz;
-    float R[12];
     R[0] = a * sc.s0;
     const float two_s1 = 2.0f * sc.s1;
     R[1] = (a * ox - fd * dx) * two_s1; R[2] = (a * oy - fd * dy) * two_s1; R[3] = (a * oz - fd * dz) * two_s1;
@@ -238,6 +237,15 @@ __device__ __forceinline__ void ray_features(float ox, float oy, float oz, float
         for (int k = 0; k < 10; ++k) R[k] = 0.0f;
         R[10] = -1.0f;
     }
+}
+
+// Three-product form (tools/probe_umma_filter.cu): hi[8] / lo[8] hold 16 fp16 each (features 0..10, then zeros), for
+// D = A_hi B_hi^T + A_hi B_lo^T + A_lo B_hi^T.
+__device__ __forceinline__ void ray_features(float ox, float oy, float oz, float dx, float dy, float dz, bool live, float sigma, const FeatScale sc,
+                                             uint32_t (&hi)[8], uint32_t (&lo)[8])
+{
+    float R[12];
+    ray_feature_values(ox, oy, oz, dx, dy, dz, live, sigma, sc, R);
 #pragma unroll
     for (int p = 0; p < 6; ++p) {
         const __half2 h = __floats2half2_rn(R[2 * p], R[2 * p + 1]);
@@ -246,6 +254,37 @@ __device__ __forceinline__ void ray_features(float ox, float oy, float oz, float
         lo[p] = pack_h2(R[2 * p] - back.x, R[2 * p + 1] - back.y);
     }
     hi[6] = hi[7] = lo[6] = lo[7] = 0u;
+}
+
+// Two-product form (the product kernels).  The three products hold 11 + 10 + 11 = 32 non-zero terms (S_10 is a power of two:
+// its lo part is zero) — exactly two K = 16 instructions when the K slots are shared:
+//     row1 = [ hi_0..hi_9 | hi_10  lo_10 | lo_0..lo_3 ]   against   B1 = [ Bhi_0..Bhi_9 | Bhi_10 Bhi_10 | Bhi_0..Bhi_3 ]
+//     row2 = [ hi_0..hi_9 | lo_4..lo_9 ]                   against   B2 = [ Blo_0..Blo_9 | Bhi_4..Bhi_9 ]
+// row2 . B2 (cross terms only) is issued first, row1 . B1 (all of hi.hi) last — see make_idesc_f16_f16.  b2_feature() is the
+// matching sphere-side slot map.
+__device__ __forceinline__ void ray_rows(float ox, float oy, float oz, float dx, float dy, float dz, bool live, float sigma, const FeatScale sc,
+                                         uint32_t (&row1)[8], uint32_t (&row2)[8])
+{
+    float R[12];
+    ray_feature_values(ox, oy, oz, dx, dy, dz, live, sigma, sc, R);
+    uint32_t lo[5];
+#pragma unroll
+    for (int p = 0; p < 5; ++p) {
+        const __half2 h = __floats2half2_rn(R[2 * p], R[2 * p + 1]);
+        const float2 back = __half22float2(h);
+        row1[p] = row2[p] = *reinterpret_cast<const uint32_t*>(&h);
+        lo[p] = pack_h2(R[2 * p] - back.x, R[2 * p + 1] - back.y);
+    }
+    const float h10 = __half2float(__float2half_rn(R[10]));
+    row1[5] = pack_h2(h10, R[10] - h10);
+    row1[6] = lo[0]; row1[7] = lo[1];
+    row2[5] = lo[2]; row2[6] = lo[3]; row2[7] = lo[4];
+}
+// K slot s of B block `blk` (0: B1, 1: B2) holds feature *feat of the sphere, its lo part when *is_lo
+__host__ __device__ inline void b2_feature(int blk, int s, int* feat, bool* is_lo)
+{
+    if (blk == 0) { *is_lo = false; *feat = s < 10 ? s : s < 12 ? 10 : s - 12; }
+    else { *is_lo = s < 10; *feat = s < 10 ? s : s - 6; }
 }
 
 }  // namespace umma

@@ -159,15 +159,8 @@ __device__ __forceinline__ void umma_issuer(const UmmaCtx& ux)
             used = true;
             const uint64_t dh = dh0 + (uint64_t)(kStep * (uint32_t)c), dl = dl0 + (uint64_t)(kStep * (uint32_t)c);
             if (elect_one()) {
-#if RT_UMMA_D16
-                mma_f16_ts(t_d, t_a, dl, idesc, 0u);                      // hi . lo   the small cross terms first: the fp16 rounding of the
-                mma_f16_ts(t_d, t_a + 8u, dh, idesc, 1u);                 // lo . hi   intermediate D costs ~2^-12 of THEM;
-                mma_f16_ts(t_d, t_a, dh, idesc, 1u);                      // hi . hi   the last sum is rounded once and keeps its sign
-#else
-                mma_f16_ts(t_d, t_a, dh, idesc, 0u);                      // hi . hi
-                mma_f16_ts(t_d, t_a, dl, idesc, 1u);                      // hi . lo
-                mma_f16_ts(t_d, t_a + 8u, dh, idesc, 1u);                 // lo . hi
-#endif
+                mma_f16_ts(t_d, t_a + 8u, dl, idesc, 0u);                 // row2 . B2: the cross terms (small: the fp16 rounding of the
+                mma_f16_ts(t_d, t_a, dh, idesc, 1u);                      // intermediate D costs ~2^-12 of THEM); row1 . B1: all of hi.hi
                 tc_commit(bar_full);
             }
             __syncwarp();
@@ -228,10 +221,10 @@ __device__ __forceinline__ HitF closest_hit_umma(UmmaCtx& ux, const SceneDev& sc
     const float sigma = sc.filter_sigma * (fabsf(o.x) + fabsf(o.y) + fabsf(o.z));     // covers the f32 error of a far origin's foot point
     const bool live = length_squared(f) < sc.filter_R2 + sigma;                        // a line that misses the bounding sphere hits nothing
     {
-        uint32_t hi[8], lo[8];
-        ray_features(f.x, f.y, f.z, dhat.x, dhat.y, dhat.z, live, sigma, sc.u_sc, hi, lo);
-        tmem_st8(ux.t_a + ux.lane_base, hi);
-        tmem_st8(ux.t_a + 8u + ux.lane_base, lo);
+        uint32_t row1[8], row2[8];
+        ray_rows(f.x, f.y, f.z, dhat.x, dhat.y, dhat.z, live, sigma, sc.u_sc, row1, row2);
+        tmem_st8(ux.t_a + ux.lane_base, row1);
+        tmem_st8(ux.t_a + 8u + ux.lane_base, row2);
     }
     tc_wait_st();
     tc_fence_before();
