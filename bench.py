@@ -52,6 +52,7 @@ CONFIGS = {
 }
 FLOP_PER_TEST = 17.0            # sphere.rs:18-25 with a and r^2 hoisted
 FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
+TENSOR_FLOP_PER_TEST = 2 * 16 * 2.0          # two tcgen05.mma of K = 16 per (ray, padded sphere), 2 FLOP per multiply-add
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE render_kernel launch of this workload on one GPU, from the ncu --set full
 # capture summarised in profiles/r1_p_render_kernel_ncu_bench_size.txt (19.56 MB read + 0.72 MB written): the scene, the
 # per-sphere records and the fixed-point accumulators; the 9.7 TFLOP of the launch run out of shared memory and registers.
@@ -184,8 +185,10 @@ def roofline_objects(world, kms, rays_total, n_spheres, npad, backend_tensor, pe
     """Two rooflines for the dominant kernel (per GPU).  The filter's work is `rays x spheres` discriminants:
       fp32  : the ALGORITHMIC figure of SURVEY §8(d), 17 FLOP per test, against the FP32 pipe (FFMA2 calibration kernel of this run).
               With the filter on the tensor cores this exceeds 1: the FP32 pipe no longer does that work.
-      tensor: the FLOP the tensor cores EXECUTE: per test 3 products (hi.hi, hi.lo, lo.hi) x K = 16 x 2 = 96, padding spheres
-              included, against the measured dense bf16/fp16 peak of MEASURED_PEAKS.json (sustained: the kernel is the whole step).
+      tensor: the FLOP the tensor cores EXECUTE: per test 2 MMAs (the 32 non-zero terms of hi.hi + hi.lo + lo.hi share two K = 16
+              instructions, rt_umma.cuh ray_rows) x K = 16 x 2 = 64, padding spheres included, against the measured dense bf16/fp16
+              peak of MEASURED_PEAKS.json (sustained: the kernel is the whole step).  Round 2 started at 3 MMAs (96): the fraction
+              went DOWN while the kernel got faster — it is a utilisation figure of a pipe that does not bound the kernel.
     """
     tests_alg = rays_total * n_spheres / world
     fp32 = {"bound": "fp32", "achieved": tests_alg * FLOP_PER_TEST / (kms * 1e-3) / 1e12, "peak": peak_fp32, "unit": "TFLOP/s",
@@ -211,12 +214,13 @@ def roofline_objects(world, kms, rays_total, n_spheres, npad, backend_tensor, pe
         except (ValueError, KeyError):
             pass
     if backend_tensor:
-        flop_exec = rays_total * npad * 96.0 / world
+        flop_exec = rays_total * npad * TENSOR_FLOP_PER_TEST / world
         main = {"bound": "tensor", "achieved": flop_exec / (kms * 1e-3) / 1e12, "peak": t_peak, "unit": "TFLOP/s", "peak_source": t_src,
-                "peak_burst": peaks.get("bf16_tflops"), "flop_per_test_executed": 96.0, "spheres_padded": npad,
-                "bound_note": "the sphere filter is a [rays x 11] x [11 x spheres] contraction on tcgen05 (fp16 hi/lo split, 3 MMAs of K = 16 per chunk, fp32 "
-                              "accumulate in TMEM); what actually limits the kernel is the sign collection on the half-rate ALU pipe (1 SHF per test) and the "
-                              "latency of the per-ray code, see DESIGN.md §1.2 and profiles/"}
+                "peak_burst": peaks.get("bf16_tflops"), "flop_per_test_executed": TENSOR_FLOP_PER_TEST, "spheres_padded": npad,
+                "bound_note": "the sphere filter is a [rays x 11] x [11 x spheres] contraction on tcgen05 (fp16 hi/lo split, 2 MMAs of K = 16 per chunk of 64 "
+                              "spheres, fp16 accumulator in TMEM: only its sign is read back, four sign bits per ALU instruction); no pipe bounds the kernel "
+                              "(issue slots 70 % busy, ALU pipe 55 %, tensor pipe ~30 %): it is bound by the latency of the per-group chain ray rows -> MMA -> "
+                              "TMEM load -> signs and of the per-ray code, see DESIGN.md §1.2 and profiles/"}
         main["frac"] = main["achieved"] / t_peak
     else:
         main = dict(fp32)
