@@ -103,6 +103,8 @@ __device__ __forceinline__ bool elect_one()
     return pred != 0u;
 }
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+// producer side of a named barrier: counts the warp's 32 threads and carries on (the consumer bar.syncs with the same count)
+__device__ __forceinline__ void named_bar_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 // barrier + OR-reduction of a predicate over the barrier's threads
 __device__ __forceinline__ bool named_bar_or(int id, int threads, bool pred)
 {

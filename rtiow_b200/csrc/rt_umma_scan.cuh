@@ -36,7 +36,16 @@ namespace rt {
 #define RT_UMMA_EW 1                          // 32-sphere words fetched from TMEM at a time (registers: 32 per word)
 #endif
 #ifndef RT_UMMA_D16
-#define RT_UMMA_D16 1                         // fp16 accumulator + packed sign collection (rt_umma.cuh, sign_word16); 0: fp32 D, one SHF per sphere
+#define RT_UMMA_D16 1                         // fp16 accumulator + packed sign collection (rt_umma.cuh, sign_word16); the only form left
+#endif
+#ifndef RT_UMMA_EMPTY_NAMED
+#define RT_UMMA_EMPTY_NAMED 1                 // "D has been read": a named barrier (bar.arrive / bar.sync) instead of an mbarrier the issuer polls
+#endif
+#ifndef RT_UMMA_BIG_AT
+#define RT_UMMA_BIG_AT -1                     // the large spheres are tested after this chunk's D was handed back (-1: before the first wait)
+#endif
+#ifndef RT_UMMA_PIPE_DRAIN
+#define RT_UMMA_PIPE_DRAIN 0                  // survivors go through the precise test inside the chunk loop, a round at a time
 #endif
 #define RT_UMMA_MIN_SMEM (120 * 1024)        // > half an SM's shared memory: one CTA per SM (each CTA allocates all of TMEM)
 
@@ -45,6 +54,7 @@ template <int G, int NC> struct UmmaShape {
     static constexpr int kRayThreads = G * 128, kThreads = G * 160;
     static constexpr int kCols = NC + 16;                        // TMEM columns per group: D (NC) + A_hi (8) + A_lo (8)
     static_assert(G * kCols <= 512, "TMEM has 512 columns");
+    static_assert(G <= 6, "named barriers: 0 = __syncthreads, 1..G the groups' votes, 7..6+G their hand-back barriers");
     static constexpr size_t kCandBytes = (size_t)kRayThreads * RT_CAND_CAP * sizeof(uint16_t);
     __host__ __device__ static constexpr size_t b_offset_bytes() { return (kCandBytes + 127) & ~(size_t)127; }
     __host__ __device__ static size_t bars_offset_bytes(int npad) { return b_offset_bytes() + 2 * RT_UMMA_B_BLOCK_BYTES(npad); }
@@ -146,7 +156,8 @@ __device__ __forceinline__ void umma_issuer(const UmmaCtx& ux)
     const uint32_t bar_afull = __shfl_sync(RT_FULL, ux.bar_afull, 0), bar_full = bar_afull + 8u, bar_empty = bar_afull + 16u;
     const uint32_t s_hi = __shfl_sync(RT_FULL, ux.s_hi, 0), s_lo = __shfl_sync(RT_FULL, ux.s_lo, 0);
     const int n_chunks = __shfl_sync(RT_FULL, ux.n_chunks, 0);
-    const uint32_t idesc = RT_UMMA_D16 ? make_idesc_f16_f16(NC) : make_idesc_f16_f32(NC);
+    const int group = __shfl_sync(RT_FULL, ux.group, 0);
+    const uint32_t idesc = make_idesc_f16_f16(NC);
     const uint64_t dh0 = make_smem_desc(s_hi, RT_UMMA_B_LBO, RT_UMMA_B_SBO), dl0 = make_smem_desc(s_lo, RT_UMMA_B_LBO, RT_UMMA_B_SBO);
     constexpr uint32_t kStep = ((uint32_t)(NC / 8) * RT_UMMA_B_SBO) >> 4;     // descriptor start-address units (16 bytes) per chunk
     uint32_t a_phase = 0, e_phase = 0; bool used = false;
@@ -155,7 +166,11 @@ __device__ __forceinline__ void umma_issuer(const UmmaCtx& ux)
         if (*ux.quit) break;
         tc_fence_after();
         for (int c = 0; c < n_chunks; ++c) {
+#if RT_UMMA_EMPTY_NAMED
+            if (used) { named_bar_sync(7 + group, 160); tc_fence_after(); }                       // the previous chunk's D has been read
+#else
             if (used) { mbar_wait(bar_empty, e_phase); e_phase ^= 1u; tc_fence_after(); }         // the previous chunk's D has been read
+#endif
             used = true;
             const uint64_t dh = dh0 + (uint64_t)(kStep * (uint32_t)c), dl = dl0 + (uint64_t)(kStep * (uint32_t)c);
             if (elect_one()) {
@@ -184,6 +199,20 @@ __device__ __forceinline__ void umma_teardown(uint32_t tmem_base)
     if ((threadIdx.x >> 5) == 0) umma::tmem_dealloc(tmem_base, 512);
 }
 
+// a ray warp is done with the chunk's D.  The issuer waits for the group's four warps on a NAMED barrier (ids 7..12, 128 ray
+// threads arriving + the issuer warp syncing): the hardware wakes it on the last arrival, where an mbarrier poll loop costs a
+// round of try_wait / branch instructions before the MMAs of the next chunk go out — and that hop is on the scan's critical
+// path (ray rows -> MMA -> commit -> TMEM load -> hand back -> MMA ...: ~900 cycles per chunk for ~90 cycles of tensor work)
+__device__ __forceinline__ void umma_hand_back(const UmmaCtx& ux)
+{
+#if RT_UMMA_EMPTY_NAMED
+    umma::named_bar_arrive(7 + ux.group, 160);
+#else
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) umma::mbar_arrive(ux.bar_empty);
+#endif
+}
+
 // Closest hit of one ray against the whole scene — the tensor-core twin of closest_hit<kSmem> (rt_scene.cuh); every one of
 // the group's 128 ray threads must call together (lanes without a ray pass anything: their result is ignored).
 // `has_ray`: this lane carries a ray.  A warp without any (the end of a frame: the queue is empty and its paths are done, while
@@ -201,8 +230,7 @@ __device__ __forceinline__ HitF closest_hit_umma(UmmaCtx& ux, const SceneDev& sc
             mbar_wait_spin(ux.bar_full, ux.full_phase); ux.full_phase ^= 1u;
             tc_fence_after();
             tc_fence_before();
-            __syncwarp();
-            if ((threadIdx.x & 31) == 0) mbar_arrive(ux.bar_empty);
+            umma_hand_back(ux);
         }
         HitF none; none.t = __int_as_float(0x7f800000); none.idx = -1; none.code = RT_SELF_NONE;
         return none;
@@ -231,29 +259,36 @@ __device__ __forceinline__ HitF closest_hit_umma(UmmaCtx& ux, const SceneDev& sc
     mbar_arrive(ux.bar_afull);
     RT_STAMP(5);
 
-    // the large spheres while the first chunk's MMAs are in flight: f32 through the cancellation-free form (big_spheres_f32);
-    // lanes whose origin defeats it, and scenes whose large spheres are not f32-representable, take the f64 routine
+    // The large spheres go into the ray warps' idle time: a chunk's round trip (hand D back -> issuer -> MMAs -> commit) is ~900
+    // cycles of which the sign collection fills a third, so the test runs after chunk RT_UMMA_BIG_AT's D was handed back
+    // instead of before the first wait (where it delayed every chunk).  f32 through the cancellation-free form
+    // (big_spheres_f32); lanes whose origin defeats it, and scenes whose large spheres are not f32-representable, take the f64 routine
     double t_big = __longlong_as_double(0x7ff0000000000000LL); int i_big = -1, c_big = RT_SELF_NONE;
-    if (sc.nb > 0) {
-        bool need64 = sc.bigf == nullptr;
-        if (!need64) { float tf; big_spheres_f32(sc.bigf, sc.big_idx, sc.nb, o, dhat, t_min, self_code, self_n, &tf, &i_big, &c_big, &need64); t_big = (double)tf; }
-        if (need64) big_spheres_best(sc.big, sc.big_idx, sc.nb, o, dhat, t_min, self_code, self_n, &t_big, &i_big, &c_big);
-    }
+    auto big_spheres = [&]() {
+        if (sc.nb > 0) {
+            bool need64 = sc.bigf == nullptr;
+            if (!need64) { float tf; big_spheres_f32(sc.bigf, sc.big_idx, sc.nb, o, dhat, t_min, self_code, self_n, &tf, &i_big, &c_big, &need64); t_big = (double)tf; }
+            if (need64) big_spheres_best(sc.big, sc.big_idx, sc.nb, o, dhat, t_min, self_code, self_n, &t_big, &i_big, &c_big);
+        }
+    };
+    if (RT_UMMA_BIG_AT < 0) big_spheres();
 
     RT_STAMP(6);
-    int nc = 0;
+    int nc = 0, nd = 0;                                                        // candidates listed / already through the precise test
     for (int c = 0; c < ux.n_chunks; ++c) {
         mbar_wait_spin(ux.bar_full, ux.full_phase); ux.full_phase ^= 1u;
         RT_STAMP(10 + c);
         tc_fence_after();
-#if RT_UMMA_D16
+#if !RT_UMMA_D16
+#error "the fp32-accumulator scan (one SHF per sphere) was removed; see git history before the fp16-D commit"
+#endif
         uint32_t v[NC / 32][16];
 #pragma unroll
         for (int w = 0; w < NC / 32; ++w) tmem_ld16p(ux.t_d + ux.lane_base + 32u * w, v[w]);
         tc_wait_ld();
+        RT_STAMP(40 + c);
         tc_fence_before();                                                     // hand D back to the issuer, whose next MMAs then
-        __syncwarp();                                                          // overlap the sign collection
-        if ((threadIdx.x & 31) == 0) mbar_arrive(ux.bar_empty);
+        umma_hand_back(ux);                                                    // overlap the sign collection
 #pragma unroll
         for (int w = 0; w < NC / 32; ++w) {
             unsigned pass = ~sign_word16(v[w]);                                // bit (31-k) set: sphere k of the word passed the filter
@@ -265,50 +300,27 @@ __device__ __forceinline__ HitF closest_hit_umma(UmmaCtx& ux, const SceneDev& sc
                 else if (p != self_code) { const float4 s = sc.small[p]; candidate<float, true>(o, dhat, inv_a, t_min, mk(s.x, s.y, s.z), s.w, p, &tb, &pb); }
             }
         }
-#else
-#pragma unroll
-        for (int w0 = 0; w0 < NC / 32; w0 += EW) {
-            uint32_t v[EW][32];
-#pragma unroll
-            for (int w = 0; w < EW; ++w) tmem_ld32(ux.t_d + ux.lane_base + 32u * (w0 + w), v[w]);
-            tc_wait_ld();
-            if (w0 + EW == NC / 32) {                                          // the chunk's last loads: hand D back to the issuer, whose
-                tc_fence_before();                                             // next MMAs then overlap the sign collection
-                __syncwarp();
-                if ((threadIdx.x & 31) == 0) mbar_arrive(ux.bar_empty);
-            }
-            // sign bits -> 32-sphere words.  SHF runs on the half-rate ALU pipe with a 4-cycle dependent latency, so every word is
-            // collected as two independent 16-bit chains and the words in flight are interleaved: 2 EW chains
-            unsigned mh[EW], ml[EW];
-#pragma unroll
-            for (int w = 0; w < EW; ++w) { mh[w] = 0; ml[w] = 0; }
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-#pragma unroll
-                for (int w = 0; w < EW; ++w) {
-                    mh[w] = __funnelshift_l(v[w][k], mh[w], 1);                // spheres 0..15 of the word
-                    ml[w] = __funnelshift_l(v[w][16 + k], ml[w], 1);           // spheres 16..31
-                }
-            }
-#pragma unroll
-            for (int w = 0; w < EW; ++w) {
-                unsigned pass = ~__byte_perm(ml[w], mh[w], 0x5410);            // bit (31-k) set: sphere k of the word passed the filter
-                while (pass) {
-                    const int k = __clz(pass);
-                    pass &= ~(0x80000000u >> k);
-                    const int p = c * NC + (w0 + w) * 32 + k;
-                    if (nc < RT_CAND_CAP) { ux.cand[nc * kStride] = (uint16_t)p; ++nc; }
-                    else if (p != self_code) { const float4 s = sc.small[p]; candidate<float, true>(o, dhat, inv_a, t_min, mk(s.x, s.y, s.z), s.w, p, &tb, &pb); }
-                }
-            }
+        RT_STAMP(70 + c);
+        if (RT_UMMA_BIG_AT >= 0 && c == (RT_UMMA_BIG_AT < ux.n_chunks ? RT_UMMA_BIG_AT : ux.n_chunks - 1)) big_spheres();
+#if RT_UMMA_PIPE_DRAIN
+        // one round of the survivors' precise test while the next chunk's MMAs run, as soon as some lane has two waiting
+        if (c + 1 < ux.n_chunks && __reduce_max_sync(RT_FULL, nc - nd) >= 2) {
+            const bool h0 = nd < nc, h1 = nd + 1 < nc;
+            const int p0 = h0 ? ux.cand[nd * kStride] : self_code, p1 = h1 ? ux.cand[(nd + 1) * kStride] : self_code;
+            const bool g0 = h0 && p0 != self_code, g1 = h1 && p1 != self_code;
+            const float4 s0 = g0 ? sc.small[p0] : make_float4(0.f, 0.f, 0.f, 0.f), s1 = g1 ? sc.small[p1] : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (g0) candidate<float, true>(o, dhat, inv_a, t_min, mk(s0.x, s0.y, s0.z), s0.w, p0, &tb, &pb);
+            if (g1) candidate<float, true>(o, dhat, inv_a, t_min, mk(s1.x, s1.y, s1.z), s1.w, p1, &tb, &pb);
+            nd = min(nd + 2, nc);
         }
 #endif
     }
     RT_STAMP(7);
     // survivors through the precise test, the warp in lock step, TWO per round: the test is one dependent chain (load, ~25 FP
     // operations, a MUFU), so two independent ones per lane halve the rounds' latency (the drain was 11 % of an iteration)
-    const int nmax = __reduce_max_sync(RT_FULL, nc);
-    for (int k = 0; k < nmax; k += 2) {
+    const int nmax = __reduce_max_sync(RT_FULL, nc - nd);
+    for (int kk = 0; kk < nmax; kk += 2) {
+        const int k = nd + kk;
         const bool h0 = k < nc, h1 = k + 1 < nc;
         const int p0 = h0 ? ux.cand[k * kStride] : self_code, p1 = h1 ? ux.cand[(k + 1) * kStride] : self_code;
         const bool g0 = h0 && p0 != self_code, g1 = h1 && p1 != self_code;

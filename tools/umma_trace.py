@@ -23,12 +23,16 @@ with capi.Context(1) as ctx:
     print(f"kernel {st['kernel_ms']:.3f} ms; {n} stamps")
     tags, clk = a[:, 0], a[:, 1]
     starts = np.nonzero(tags == 1)[0]
-    rows = []
+    rows = []; fine = []
     for s, e in zip(starts[2:-1], starts[3:]):             # skip the first two iterations (cold)
         seg = {int(t): int(c) for t, c in zip(tags[s:e], clk[s:e])}
         if not all(k in seg for k in (1, 2, 3, 4, 5, 6, 10, 7, 8, 9)):
             continue
-        chunks = [seg[k] for k in sorted(k for k in seg if k >= 10)]
+        chunks = [seg[k] for k in sorted(k for k in seg if 10 <= k < 40)]
+        lds = [seg[k] for k in sorted(k for k in seg if 40 <= k < 70)]
+        cols = [seg[k] for k in sorted(k for k in seg if 70 <= k < 100)]
+        if len(lds) == len(chunks) == len(cols):
+            fine.append([np.mean(np.array(lds) - np.array(chunks)), np.mean(np.array(cols) - np.array(lds)), np.mean(np.array(chunks[1:]) - np.array(cols[:-1]))])
         rows.append([seg[2] - seg[1], seg[3] - seg[2], seg[4] - seg[3], seg[5] - seg[4], seg[6] - seg[5], chunks[0] - seg[6],
                      (chunks[-1] - chunks[0]) / max(len(chunks) - 1, 1), seg[7] - chunks[-1], seg[8] - seg[7], seg[9] - seg[8], clk[e] - seg[1]])
     r = np.array(rows, float)
@@ -37,3 +41,6 @@ with capi.Context(1) as ctx:
     for i, nm in enumerate(names):
         print(f"  {nm:42s} mean {r[:, i].mean():8.0f}  median {np.median(r[:, i]):8.0f}  p90 {np.percentile(r[:, i], 90):8.0f}")
     print(f"  iterations analysed: {len(r)}")
+    if fine:
+        f = np.array(fine, float).mean(axis=0)
+        print(f"  inside a chunk (mean): full passed -> TMEM loads done {f[0]:.0f}; -> D handed back + signs collected + survivors listed {f[1]:.0f}; -> next full passed (waiting) {f[2]:.0f}")
