@@ -165,6 +165,8 @@ __device__ __forceinline__ void umma_issuer(const UmmaCtx& ux)
         mbar_wait(bar_afull, a_phase, RT_UMMA_AFULL_BACKOFF_NS); a_phase ^= 1u;   // all 128 feature rows are in TMEM — or the group is done
         if (*ux.quit) break;
         tc_fence_after();
+        uint64_t dh = dh0, dl = dl0;                                           // the chunk's B descriptors, stepped after the issue so that
+#pragma unroll 1                                                               // nothing but the MMAs stands between the barrier and the tensor pipe
         for (int c = 0; c < n_chunks; ++c) {
 #if RT_UMMA_EMPTY_NAMED
             if (used) { named_bar_sync(7 + group, 160); tc_fence_after(); }                       // the previous chunk's D has been read
@@ -172,13 +174,13 @@ __device__ __forceinline__ void umma_issuer(const UmmaCtx& ux)
             if (used) { mbar_wait(bar_empty, e_phase); e_phase ^= 1u; tc_fence_after(); }         // the previous chunk's D has been read
 #endif
             used = true;
-            const uint64_t dh = dh0 + (uint64_t)(kStep * (uint32_t)c), dl = dl0 + (uint64_t)(kStep * (uint32_t)c);
             if (elect_one()) {
                 mma_f16_ts(t_d, t_a + 8u, dl, idesc, 0u);                 // row2 . B2: the cross terms (small: the fp16 rounding of the
                 mma_f16_ts(t_d, t_a, dh, idesc, 1u);                      // intermediate D costs ~2^-12 of THEM); row1 . B1: all of hi.hi
                 tc_commit(bar_full);
             }
             __syncwarp();
+            dh += kStep; dl += kStep;
         }
     }
 }
