@@ -46,34 +46,7 @@ enum { F_MMA = 1, F_SIGN = 2, F_DUMP = 4, F_SWAP = 8, F_NOLD = 16, F_TRACE = 32,
 // back as packed halves (tcgen05.ld ... .pack::16b: 32 spheres in 16 registers) and the sign bits are collected FOUR per
 // instruction: PRMT with sign replication turns two registers into four sign bytes, a LOP3 bit-select tree interleaves eight
 // such words into one 32-sphere mask: 8 PRMT + 7 LOP3 per word instead of 32 SHF.
-__host__ __device__ constexpr uint32_t make_idesc_f16_f16(int n)
-{
-    return (0u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-}
-__device__ __forceinline__ void tmem_ld16p(uint32_t taddr, uint32_t (&v)[16])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.pack::16b.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
-          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr) : "memory");
-}
-// bytes 1 and 3 of a, bytes 1 and 3 of b, each replaced by eight copies of its sign bit
-__device__ __forceinline__ uint32_t sign_bytes(uint32_t a, uint32_t b)
-{
-    uint32_t d; asm("prmt.b32 %0, %1, %2, 0xfdb9;" : "=r"(d) : "r"(a), "r"(b)); return d;
-}
-// 16 packed registers (32 halves) -> 32 sign bits: bit 8 b + j = sign of half (4 j + b)
-__device__ __forceinline__ uint32_t sign_word16(const uint32_t (&v)[16])
-{
-    uint32_t d[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) d[j] = sign_bytes(v[2 * j], v[2 * j + 1]);
-    const uint32_t x0 = (d[0] & 0x55555555u) | (d[1] & 0xaaaaaaaau), x1 = (d[2] & 0x55555555u) | (d[3] & 0xaaaaaaaau);
-    const uint32_t x2 = (d[4] & 0x55555555u) | (d[5] & 0xaaaaaaaau), x3 = (d[6] & 0x55555555u) | (d[7] & 0xaaaaaaaau);
-    const uint32_t y0 = (x0 & 0x33333333u) | (x1 & 0xccccccccu), y1 = (x2 & 0x33333333u) | (x3 & 0xccccccccu);
-    return (y0 & 0x0f0f0f0fu) | (y1 & 0xf0f0f0f0u);
-}
+// make_idesc_f16_f16, tmem_ld16p, sign_word16: rt_umma.cuh (the product kernels use them since this probe passed)
 
 template <int G, int NC, int NBUF, int FLAGS>
 __global__ void __launch_bounds__(G * 160, 1) probe_kernel(const ProbeArgs a)
@@ -531,6 +504,7 @@ int main(int argc, char** argv)
     // ---- raw MMA rate (one CTA) ----
     {
         long long* d_rate; CK(cudaMalloc(&d_rate, 16));
+        run_rate<32, 1, 1>(d_b, npad, d_rate, smem_bytes); run_rate<48, 1, 1>(d_b, npad, d_rate, smem_bytes);
         run_rate<64, 1, 1>(d_b, npad, d_rate, smem_bytes); run_rate<64, 0, 1>(d_b, npad, d_rate, smem_bytes);
         run_rate<128, 1, 1>(d_b, npad, d_rate, smem_bytes); run_rate<256, 1, 1>(d_b, npad, d_rate, smem_bytes);
         run_rate<96, 1, 1>(d_b, npad, d_rate, smem_bytes); run_rate<64, 1, 0>(d_b, npad, d_rate, smem_bytes); run_rate<256, 1, 0>(d_b, npad, d_rate, smem_bytes);
@@ -539,6 +513,8 @@ int main(int argc, char** argv)
     // ---- throughput ----
     run<6, 64, 1, F_MMA | F_SIGN>("full", a, n_real, smem_bytes, sms);
     run<6, 64, 1, F_MMA | F_SIGN | F_D16>("full, fp16 D + PRMT/LOP3 signs", a, n_real, smem_bytes, sms);
+    run<6, 32, 2, F_MMA | F_SIGN | F_D16>("full, fp16 D + PRMT/LOP3 signs", a, n_real, smem_bytes, sms);
+    run<6, 32, 1, F_MMA | F_SIGN | F_D16>("full, fp16 D + PRMT/LOP3 signs", a, n_real, smem_bytes, sms);
     run<4, 64, 1, F_MMA | F_SIGN | F_D16>("full, fp16 D + PRMT/LOP3 signs", a, n_real, smem_bytes, sms);
     run<3, 64, 2, F_MMA | F_SIGN | F_D16>("full, fp16 D + PRMT/LOP3 signs", a, n_real, smem_bytes, sms);
     run<3, 128, 1, F_MMA | F_SIGN | F_D16>("full, fp16 D + PRMT/LOP3 signs", a, n_real, smem_bytes, sms);
