@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(G * 160, 1) render_kernel_umma(const RenderArg
 
             n_rays_w += __popc(__ballot_sync(RT_FULL, active));              // world.hit call count (main.rs:44)
             RT_STAMP(4);
-            const HitF h = closest_hit_umma<G, NC, RT_UMMA_EW>(ux, a.scene, ps.o, ps.dhat, ps.tmin_n, ps.self_code, ps.self_n, active);
+            const HitF h = closest_hit_umma<G, NC>(ux, a.scene, ps.o, ps.dhat, ps.tmin_n, ps.self_code, ps.self_n, active);
             RT_STAMP(9);
             if (active) {
                 if (h.idx < 0) accumulate(a, acc_lp, ps.thr * sky<float, true>(ps.dhat));                    // miss: sky (main.rs:54-56)

@@ -32,20 +32,11 @@ namespace rt {
 #ifndef RT_UMMA_AFULL_BACKOFF_NS
 #define RT_UMMA_AFULL_BACKOFF_NS 0            // the issuer's sleep between polls while its group is in the per-ray phase (0, 100, 400 ns measured the same)
 #endif
-#ifndef RT_UMMA_EW
-#define RT_UMMA_EW 1                          // 32-sphere words fetched from TMEM at a time (registers: 32 per word)
-#endif
 #ifndef RT_UMMA_D16
 #define RT_UMMA_D16 1                         // fp16 accumulator + packed sign collection (rt_umma.cuh, sign_word16); the only form left
 #endif
 #ifndef RT_UMMA_EMPTY_NAMED
 #define RT_UMMA_EMPTY_NAMED 1                 // "D has been read": a named barrier (bar.arrive / bar.sync) instead of an mbarrier the issuer polls
-#endif
-#ifndef RT_UMMA_BIG_AT
-#define RT_UMMA_BIG_AT -1                     // the large spheres are tested after this chunk's D was handed back (-1: before the first wait)
-#endif
-#ifndef RT_UMMA_PIPE_DRAIN
-#define RT_UMMA_PIPE_DRAIN 0                  // survivors go through the precise test inside the chunk loop, a round at a time
 #endif
 #define RT_UMMA_MIN_SMEM (120 * 1024)        // > half an SM's shared memory: one CTA per SM (each CTA allocates all of TMEM)
 
@@ -220,7 +211,7 @@ __device__ __forceinline__ void umma_hand_back(const UmmaCtx& ux)
 // `has_ray`: this lane carries a ray.  A warp without any (the end of a frame: the queue is empty and its paths are done, while
 // a neighbour's 50-bounce path keeps the group scanning) only keeps the group's barriers moving — no feature rows, no TMEM
 // loads, no sign collection — so that the warps that still work get the SM to themselves and the frame's tail gets shorter.
-template <int G, int NC, int EW = NC / 32>
+template <int G, int NC>
 __device__ __forceinline__ HitF closest_hit_umma(UmmaCtx& ux, const SceneDev& sc, V3<float> o, V3<float> dhat, float t_min, int self_code, V3<float> self_n,
                                                  bool has_ray = true)
 {
@@ -237,7 +228,6 @@ __device__ __forceinline__ HitF closest_hit_umma(UmmaCtx& ux, const SceneDev& sc
         HitF none; none.t = __int_as_float(0x7f800000); none.idx = -1; none.code = RT_SELF_NONE;
         return none;
     }
-    static_assert(EW >= 1 && (NC / 32) % EW == 0, "EW = 32-sphere words loaded from TMEM at a time");
     constexpr int kStride = UmmaShape<G, NC>::kRayThreads;
     const float inv_a = 2.0f - length_squared(dhat);           // 1/a for a = 1 + e, |e| < 1e-6
     float tb = __int_as_float(0x7f800000);                     // f64::INFINITY at main.rs:44
@@ -261,22 +251,18 @@ __device__ __forceinline__ HitF closest_hit_umma(UmmaCtx& ux, const SceneDev& sc
     mbar_arrive(ux.bar_afull);
     RT_STAMP(5);
 
-    // The large spheres go into the ray warps' idle time: a chunk's round trip (hand D back -> issuer -> MMAs -> commit) is ~900
-    // cycles of which the sign collection fills a third, so the test runs after chunk RT_UMMA_BIG_AT's D was handed back
-    // instead of before the first wait (where it delayed every chunk).  f32 through the cancellation-free form
-    // (big_spheres_f32); lanes whose origin defeats it, and scenes whose large spheres are not f32-representable, take the f64 routine
+    // the large spheres while the first chunk's MMAs are in flight (later, inside the chunk loop, they delay the warp's hand-backs:
+    // DESIGN.md §7.1): f32 through the cancellation-free form (big_spheres_f32); lanes whose origin defeats it, and scenes whose
+    // large spheres are not f32-representable, take the f64 routine
     double t_big = __longlong_as_double(0x7ff0000000000000LL); int i_big = -1, c_big = RT_SELF_NONE;
-    auto big_spheres = [&]() {
-        if (sc.nb > 0) {
-            bool need64 = sc.bigf == nullptr;
-            if (!need64) { float tf; big_spheres_f32(sc.bigf, sc.big_idx, sc.nb, o, dhat, t_min, self_code, self_n, &tf, &i_big, &c_big, &need64); t_big = (double)tf; }
-            if (need64) big_spheres_best(sc.big, sc.big_idx, sc.nb, o, dhat, t_min, self_code, self_n, &t_big, &i_big, &c_big);
-        }
-    };
-    if (RT_UMMA_BIG_AT < 0) big_spheres();
+    if (sc.nb > 0) {
+        bool need64 = sc.bigf == nullptr;
+        if (!need64) { float tf; big_spheres_f32(sc.bigf, sc.big_idx, sc.nb, o, dhat, t_min, self_code, self_n, &tf, &i_big, &c_big, &need64); t_big = (double)tf; }
+        if (need64) big_spheres_best(sc.big, sc.big_idx, sc.nb, o, dhat, t_min, self_code, self_n, &t_big, &i_big, &c_big);
+    }
 
     RT_STAMP(6);
-    int nc = 0, nd = 0;                                                        // candidates listed / already through the precise test
+    int nc = 0;
     for (int c = 0; c < ux.n_chunks; ++c) {
         mbar_wait_spin(ux.bar_full, ux.full_phase); ux.full_phase ^= 1u;
         RT_STAMP(10 + c);
@@ -303,26 +289,12 @@ __device__ __forceinline__ HitF closest_hit_umma(UmmaCtx& ux, const SceneDev& sc
             }
         }
         RT_STAMP(70 + c);
-        if (RT_UMMA_BIG_AT >= 0 && c == (RT_UMMA_BIG_AT < ux.n_chunks ? RT_UMMA_BIG_AT : ux.n_chunks - 1)) big_spheres();
-#if RT_UMMA_PIPE_DRAIN
-        // one round of the survivors' precise test while the next chunk's MMAs run, as soon as some lane has two waiting
-        if (c + 1 < ux.n_chunks && __reduce_max_sync(RT_FULL, nc - nd) >= 2) {
-            const bool h0 = nd < nc, h1 = nd + 1 < nc;
-            const int p0 = h0 ? ux.cand[nd * kStride] : self_code, p1 = h1 ? ux.cand[(nd + 1) * kStride] : self_code;
-            const bool g0 = h0 && p0 != self_code, g1 = h1 && p1 != self_code;
-            const float4 s0 = g0 ? sc.small[p0] : make_float4(0.f, 0.f, 0.f, 0.f), s1 = g1 ? sc.small[p1] : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (g0) candidate<float, true>(o, dhat, inv_a, t_min, mk(s0.x, s0.y, s0.z), s0.w, p0, &tb, &pb);
-            if (g1) candidate<float, true>(o, dhat, inv_a, t_min, mk(s1.x, s1.y, s1.z), s1.w, p1, &tb, &pb);
-            nd = min(nd + 2, nc);
-        }
-#endif
     }
     RT_STAMP(7);
     // survivors through the precise test, the warp in lock step, TWO per round: the test is one dependent chain (load, ~25 FP
     // operations, a MUFU), so two independent ones per lane halve the rounds' latency (the drain was 11 % of an iteration)
-    const int nmax = __reduce_max_sync(RT_FULL, nc - nd);
-    for (int kk = 0; kk < nmax; kk += 2) {
-        const int k = nd + kk;
+    const int nmax = __reduce_max_sync(RT_FULL, nc);
+    for (int k = 0; k < nmax; k += 2) {
         const bool h0 = k < nc, h1 = k + 1 < nc;
         const int p0 = h0 ? ux.cand[k * kStride] : self_code, p1 = h1 ? ux.cand[(k + 1) * kStride] : self_code;
         const bool g0 = h0 && p0 != self_code, g1 = h1 && p1 != self_code;

@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(G * 160, 1) hitlist_kernel_umma(SceneDev sc, i
         if (live) { o = ld3<float>(orig, i); d = ld3<float>(dir, i); }
         const float len = length(d), inv_len = 1.0f / len;
         const V3<float> dhat = d * inv_len;
-        const HitF h = closest_hit_umma<G, NC, RT_UMMA_EW>(ux, sc, o, dhat, (float)t_min * len, RT_SELF_NONE, mk<float>(0, 1, 0));
+        const HitF h = closest_hit_umma<G, NC>(ux, sc, o, dhat, (float)t_min * len, RT_SELF_NONE, mk<float>(0, 1, 0));
         umma_group_quit(ux);
         if (live) {
             V3<float> pp = mk<float>(0, 0, 0), nn = mk<float>(0, 0, 0); bool ff = false;
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(G * 160, 1) ray_color_kernel_umma(SceneDev sc,
                 if (trace_ray) { double* tr = trace_ray + ((size_t)i * max_depth + nr) * 6; tr[0] = ps.o.x; tr[1] = ps.o.y; tr[2] = ps.o.z; tr[3] = ps.dhat.x; tr[4] = ps.dhat.y; tr[5] = ps.dhat.z; }
                 ++nr;                                                             // world.hit call count (main.rs:44)
             }
-            const HitF h = closest_hit_umma<G, NC, RT_UMMA_EW>(ux, sc, ps.o, ps.dhat, ps.tmin_n, ps.self_code, ps.self_n, active);
+            const HitF h = closest_hit_umma<G, NC>(ux, sc, ps.o, ps.dhat, ps.tmin_n, ps.self_code, ps.self_n, active);
             if (!active) continue;
             if (trace_idx) trace_idx[(size_t)i * max_depth + nr - 1] = h.idx;
             if (h.idx < 0) { result = ps.thr * sky<float, true>(ps.dhat); active = false; continue; }         // main.rs:54-56

@@ -2,7 +2,7 @@
 # The multi-GPU measurement table of one box (run under `gpurun --gpus 8`): tests, then bench.py lines for BASELINE configs[1] and [4]
 # at 1/2/4/8 GPUs (one process per GPU under torchrun, gather inside librtiow_cuda.so), the NCCL-gather variant, and the one-process
 # lines (rtiow_ctx_create(N)).  Every JSON line lands in gpurun_out/scale_<tag>_*.json.   Usage: tools/scale_run.sh <tag> [max_gpus]
-tag=${1:-x}; maxn=${2:-8}
+tag=${1:-x}; maxn=${2:-8}; quick=${3:-0}     # quick=1: tests, cfg2 at 1/2/4/8, cfg5 and the one-process line at 8 only (GPU-minutes are charged x8)
 run() { # name, n, extra args...
   name=$1; n=$2; shift 2
   if [ "$n" = 1 ]; then timeout 600 python bench.py --gpus 1 "$@" > gpurun_out/scale_${tag}_${name}.json 2> gpurun_out/scale_${tag}_${name}.err
@@ -19,6 +19,11 @@ PY
 nvidia-smi -L | wc -l
 timeout 900 python -m pytest tests/test_multirank_nccl_gpu.py tests/test_host_and_multigpu_gpu.py -q -m gpu -rs > gpurun_out/scale_${tag}_tests.log 2>&1; tail -6 gpurun_out/scale_${tag}_tests.log
 for n in 1 2 4 8; do [ $n -le $maxn ] && run cfg2_n$n $n --steps 5 --warmup 3 --no-cpu-baseline; done
+if [ "$quick" = 1 ]; then
+  [ 8 -le $maxn ] && run cfg5_n8 8 --config cfg5 --steps 2 --warmup 3 --no-cpu-baseline
+  [ 8 -le $maxn ] && { timeout 600 python bench.py --inproc --gpus 8 --steps 5 --warmup 3 > gpurun_out/scale_${tag}_inproc_n8.json 2> gpurun_out/scale_${tag}_inproc_n8.err; cut -c1-160 gpurun_out/scale_${tag}_inproc_n8.json; }
+  exit 0
+fi
 [ 8 -le $maxn ] && run cfg2_n8_nccl 8 --steps 5 --warmup 3 --gather nccl
 [ 2 -le $maxn ] && run cfg2_n2_nccl 2 --steps 5 --warmup 3 --gather nccl
 for n in 1 2 4 8; do [ $n -le $maxn ] && run cfg5_n$n $n --config cfg5 --steps 2 --warmup 3 --no-cpu-baseline; done
