@@ -130,7 +130,8 @@ class ClockSampler:
 def make_config(args, n_spheres):
     """the workload, identical for both arms (the driver compares it): everything else goes to `impl_detail`"""
     return {"workload": args.workload, "width": args.width, "height": args.height, "spp": args.spp, "max_depth": WORKLOAD["max_depth"],
-            "n_spheres": n_spheres, "scene_seed": WORKLOAD["scene_seed"], "sample_seed": WORKLOAD["sample_seed"]}
+            "n_spheres": n_spheres, "scene_seed": WORKLOAD["scene_seed"], "sample_seed": WORKLOAD["sample_seed"],
+            "cache": "GPU arm: L2 flushed (160 MiB device fill) between timed steps"}
 
 
 # ----------------------------------------------------------------------------------------------- CPU arms
@@ -257,7 +258,7 @@ def run_ours(args, rank, local_rank, world):
     cam = capi.camera_new((13, 2, 3), (0, 0, 0), (0, 1, 0), 20.0, W / H, 0.1, 10.0)
     prm = capi.default_params(width=W, height=H, spp=spp, max_depth=WORKLOAD["max_depth"], t_min=WORKLOAD["t_min"], seed=WORKLOAD["sample_seed"],
                               tile_rows=args.tile_rows)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)        # > 126 MB L2
+    flush = torch.empty(160 * 1024 * 1024, dtype=torch.uint8, device=dev)        # > 126 MB L2
     # One stream for everything: the library works on it (rtiow_ctx_set_stream), so torch's L2-flush fills and the timing events
     # are ordered with the library's kernels and NCCL calls.
     stream = torch.cuda.Stream(dev)
@@ -312,11 +313,15 @@ def run_ours(args, rank, local_rank, world):
     kernel_ms, rays = [], []
     barrier()
     e0.record(stream)
+    # the K frames go onto the stream back to back (rtiow_render_rank_enqueue: kernel, epilogue / gather, frame-complete barrier; no
+    # host round trip per frame — at 8 GPUs a frame is 10 ms and a stream synchronisation plus four launch latencies are 1 % of it);
+    # the library times every frame's kernel with its own event pair and rtiow_ctx_synchronize returns the mean
     for _ in range(args.steps):
         flush.fill_(1)                                                             # evict L2 between timed iterations
-        st = step_device()
-        kernel_ms.append(st["kernel_ms"]); rays.append(st["rays_traced"])
+        ctx.render_rank_enqueue(cam, prm)
     e1.record(stream)
+    st = ctx.synchronize()
+    kernel_ms.append(st["kernel_ms"]); rays.append(st["rays_traced"])
     barrier()
     total_ms = maxr(e0.elapsed_time(e1))
     clk = clocks.stop() if rank == 0 else None
@@ -361,7 +366,8 @@ def run_ours(args, rank, local_rank, world):
             "config": make_config(args, n_spheres),
             "impl_detail": {"tile_rows": args.tile_rows, "scan_backend": "tensor (tcgen05)" if backend_tensor else "fp32 (FFMA2)",
                             "parallelism": f"interleaved row tiles x{world}; {gather_note}",
-                            "l2": "256 MiB device buffer rewritten between timed steps (inside the timed region, ~0.1 ms)"},
+                            "l2": "160 MiB device buffer (> the 126 MB L2) rewritten between timed steps, inside the timed region (~0.03 ms)",
+                            "steps": "rtiow_render_rank_enqueue x K on one stream, then rtiow_ctx_synchronize: no host synchronisation between frames"},
             "clocks": clk,
             "e2e": {"value": paths / (e2e_ms * 1e-3) / 1e6, "unit": "Mpaths/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": scene_bytes + 176 + 48, "d2h_bytes_per_step": W * H * 4 + 16,

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RTIOW_ABI_VERSION 3
+#define RTIOW_ABI_VERSION 4
 
 typedef enum {
     RTIOW_OK = 0,
@@ -173,6 +173,13 @@ int rtiow_render_rank(rtiow_ctx* ctx, const rtiow_camera* cam, const rtiow_param
 /* the same, leaving the frame in DEVICE memory: *d_frame = the whole frame on rank 0 (NCCL gather: on every rank; FUSED: NULL
  * on ranks > 0), owned by the ctx and valid until its next render. */
 int rtiow_render_rank_device(rtiow_ctx* ctx, const rtiow_camera* cam, const rtiow_params* p, const void** d_frame, rtiow_stats* stats);
+/* Frames back to back (an animation loop; the reference renders one frame per process, main.rs:104-149, so this replaces nothing
+ * there): rtiow_render_rank_device WITHOUT the host synchronisation — kernel, epilogue / gather and the frame-complete barrier are
+ * enqueued on the ctx's stream and the call returns.  *d_frame as above; with the FUSED gather two frame buffers alternate, so a
+ * frame stays valid until the second-next enqueue.  rtiow_ctx_synchronize waits for everything enqueued; its stats (may be NULL)
+ * carry the MEAN kernel_ms of the frames enqueued since the last synchronize and the paths / rays of the last one. */
+int rtiow_render_rank_enqueue(rtiow_ctx* ctx, const rtiow_camera* cam, const rtiow_params* p, const void** d_frame);
+int rtiow_ctx_synchronize(rtiow_ctx* ctx, rtiow_stats* stats);
 
 /* --- lower-level one-process-per-GPU pieces for callers that own the gather (rank r of world G renders rows {y : (y / tile_rows) % G == r}) ---- */
 /* bytes of one rank's tile buffer (equal on every rank; padded when the tile count does not divide) */

@@ -16,7 +16,7 @@ from . import build as _build
 OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_NCCL, ERR_NO_DEVICE, ERR_NOMEM, ERR_CANCELLED = 0, -1, -2, -3, -4, -5, -6, -7
 MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC = 0, 1, 2
 F32, F64 = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 SCAN_AUTO, SCAN_FP32, SCAN_TENSOR = 0, 1, 2
 GATHER_AUTO, GATHER_NCCL, GATHER_FUSED = 0, 1, 2
 NCCL_UNIQUE_ID_BYTES = 128
@@ -30,7 +30,7 @@ PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint3
 SYMBOLS = [
     "rtiow_abi_version", "rtiow_last_error", "rtiow_device_count", "rtiow_ctx_create", "rtiow_ctx_create_on_device",
     "rtiow_ctx_destroy", "rtiow_ctx_set_scan_backend", "rtiow_nccl_unique_id", "rtiow_ctx_create_rank", "rtiow_ctx_set_gather", "rtiow_ctx_set_stream",
-    "rtiow_ctx_gather_info", "rtiow_render_rank", "rtiow_render_rank_device", "rtiow_scene_upload", "rtiow_camera_new", "rtiow_params_default", "rtiow_render", "rtiow_render_progressive",
+    "rtiow_ctx_gather_info", "rtiow_render_rank", "rtiow_render_rank_device", "rtiow_render_rank_enqueue", "rtiow_ctx_synchronize", "rtiow_scene_upload", "rtiow_camera_new", "rtiow_params_default", "rtiow_render", "rtiow_render_progressive",
     "rtiow_tile_buffer_bytes", "rtiow_render_tiles_device", "rtiow_render_to_frame_device", "rtiow_deinterleave_device", "rtiow_sphere_hit_batch",
     "rtiow_hitlist_batch", "rtiow_scatter_batch", "rtiow_get_ray_batch", "rtiow_to_rgba_batch", "rtiow_reflect_batch",
     "rtiow_refract_batch", "rtiow_ray_color_batch", "rtiow_ray_color_trace_batch", "rtiow_sampler_batch", "rtiow_fp32_peak_probe", "rtiow_flush_l2",
@@ -120,6 +120,8 @@ def _declare(L):
         "rtiow_params_default": (None, [C.POINTER(Params)]),
         "rtiow_render": (C.c_int, [P, C.POINTER(Camera), C.POINTER(Params), P, C.POINTER(Stats)]),
         "rtiow_render_progressive": (C.c_int, [P, C.POINTER(Camera), C.POINTER(Params), C.c_uint32, PROGRESS_FN, P, P, C.POINTER(Stats)]),
+        "rtiow_render_rank_enqueue": (C.c_int, [P, C.POINTER(Camera), C.POINTER(Params), C.POINTER(C.c_void_p)]),
+        "rtiow_ctx_synchronize": (C.c_int, [P, C.POINTER(Stats)]),
         "rtiow_tile_buffer_bytes": (C.c_int, [C.POINTER(Params), C.c_int, C.POINTER(C.c_size_t)]),
         "rtiow_render_tiles_device": (C.c_int, [P, C.POINTER(Camera), C.POINTER(Params), C.c_int, C.c_int, P, P, C.POINTER(Stats)]),
         "rtiow_render_to_frame_device": (C.c_int, [P, C.POINTER(Camera), C.POINTER(Params), C.c_int, C.c_int, P, P, C.POINTER(Stats)]),
@@ -144,6 +146,16 @@ def _declare(L):
     for name, (res, args) in sig.items():
         f = getattr(L, name)
         f.restype, f.argtypes = res, args
+
+
+def device_to_host(ptr: int, nbytes: int) -> np.ndarray:
+    """tests / tools: copy `nbytes` of device memory (a frame pointer returned by render_rank_device / _enqueue) to the host"""
+    from cuda.bindings import runtime as cudart
+    out = np.empty(nbytes, np.uint8)
+    (err,) = cudart.cudaMemcpy(out.ctypes.data, ptr, nbytes, cudart.cudaMemcpyKind.cudaMemcpyDeviceToHost)
+    if int(err) != 0:
+        raise RuntimeError(f"cudaMemcpy D2H failed: {err}")
+    return out
 
 
 def _check(rc: int):
@@ -291,6 +303,18 @@ class Context:
         st = Stats(); ptr = C.c_void_p()
         _check(lib().rtiow_render_rank_device(self._h, C.byref(cam), C.byref(params), C.byref(ptr), C.byref(st)))
         return (ptr.value or 0), st.as_dict()
+
+    def render_rank_enqueue(self, cam: Camera, params: Params) -> int:
+        """rtiow_render_rank_enqueue (collective): one more frame on the ctx's stream, no host synchronisation -> device pointer or 0"""
+        ptr = C.c_void_p()
+        _check(lib().rtiow_render_rank_enqueue(self._h, C.byref(cam), C.byref(params), C.byref(ptr)))
+        return ptr.value or 0
+
+    def synchronize(self) -> dict:
+        """rtiow_ctx_synchronize: wait for everything enqueued -> stats (mean kernel_ms of the enqueued frames)"""
+        st = Stats()
+        _check(lib().rtiow_ctx_synchronize(self._h, C.byref(st)))
+        return st.as_dict()
 
     def __del__(self):
         try:

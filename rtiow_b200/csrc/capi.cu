@@ -18,6 +18,7 @@
 #include <string>
 #include <type_traits>
 #include <vector>
+#include <utility>
 
 using namespace rt;
 
@@ -75,6 +76,9 @@ struct DeviceState {
     int sms = 0;
     cudaStream_t stream = nullptr; bool owns_stream = true;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_done = nullptr;
+    // frames enqueued without a host synchronisation (rtiow_render_rank_enqueue): one event pair per frame until rtiow_ctx_synchronize
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ring; size_t ring_used = 0;
+    uint64_t enq_paths = 0; uint32_t enq_launches = 0; uint32_t enq_world = 1;
     // scene
     DevBuf<float> table; DevBuf<float4> small; DevBuf<int> small_idx; DevBuf<double4> big; DevBuf<int> big_idx;
     DevBuf<float4> sph; DevBuf<double4> sphd; DevBuf<float4> mat; DevBuf<double4> matd; DevBuf<uint8_t> kind;
@@ -325,6 +329,7 @@ extern "C" void rtiow_ctx_destroy(rtiow_ctx* c)
         if (d.ev0) cudaEventDestroy(d.ev0);
         if (d.ev1) cudaEventDestroy(d.ev1);
         if (d.ev_done) cudaEventDestroy(d.ev_done);
+        for (auto& ev : d.ring) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
         if (d.stream && d.owns_stream) cudaStreamDestroy(d.stream);
     }
     delete c;
@@ -1036,7 +1041,8 @@ static int ensure_nccl_buffers(rtiow_ctx* c, size_t tile_px, cudaStream_t st)
     return RTIOW_OK;
 }
 
-static int render_rank_impl(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_params* p, uint8_t* out_rgba, const void** d_frame_out, rtiow_stats* stats)
+static int render_rank_impl(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_params* p, uint8_t* out_rgba, const void** d_frame_out, rtiow_stats* stats,
+                            bool enqueue_only = false)
 {
     if (!c || !cam) return fail(RTIOW_ERR_INVALID_ARG, "NULL argument");
     int rc = check_params(p); if (rc) return rc;
@@ -1051,12 +1057,22 @@ static int render_rank_impl(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_p
     const size_t tile_px = (size_t)max_rows_per_rank(p->height, tile_rows_of(p), world) * p->width;
     uint32_t launches = 0;
     const uint32_t* d_final = nullptr;
+    // the events around the render kernel: the ctx's pair, or — for a frame that is only enqueued — the next pair of the ring
+    cudaEvent_t e0 = d.ev0, e1 = d.ev1;
+    if (enqueue_only) {
+        if (d.ring_used == d.ring.size()) {
+            std::pair<cudaEvent_t, cudaEvent_t> ev{ nullptr, nullptr };
+            CU(cudaEventCreate(&ev.first)); CU(cudaEventCreate(&ev.second));
+            d.ring.push_back(ev);
+        }
+        e0 = d.ring[d.ring_used].first; e1 = d.ring[d.ring_used].second;
+    }
     bool frame_here = true;                                 // d_final holds the whole frame on THIS rank
     if (world == 1) {
         CU(d.tiles.resize(tile_px));
-        CU(cudaEventRecord(d.ev0, st));
+        CU(cudaEventRecord(e0, st));
         rc = render_tiles(c, d, cam, p, 0, 1, d.tiles.p, st, &launches); if (rc) return rc;
-        CU(cudaEventRecord(d.ev1, st));
+        CU(cudaEventRecord(e1, st));
         d_final = d.tiles.p;
         c->gather_note = "single GPU: no gather";
     } else {
@@ -1073,9 +1089,9 @@ static int render_rank_impl(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_p
             // it is the frame-complete barrier.  Two frames alternate, so rank 0's copy-out of frame k is ordered (by its stream
             // and the barrier of frame k+1) before anybody writes that buffer again in frame k+2.
             uint32_t* fr = c->ipc_frame + (size_t)(c->ipc_parity & 1u) * npx; c->ipc_parity ^= 1u;
-            CU(cudaEventRecord(d.ev0, st));
+            CU(cudaEventRecord(e0, st));
             rc = render_tiles(c, d, cam, p, rank, world, nullptr, st, &launches, fr); if (rc) return rc;
-            CU(cudaEventRecord(d.ev1, st));
+            CU(cudaEventRecord(e1, st));
             rc = nccl_barrier(c, st); if (rc) return rc;
             d_final = fr; frame_here = rank == 0;
             snprintf(note, sizeof note, "one process per GPU x%u: epilogue stores into rank 0's frame over NVLink (CUDA IPC mapping made inside librtiow_cuda.so) + "
@@ -1085,9 +1101,9 @@ static int render_rank_impl(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_p
             uint32_t* tiles = c->nccl_tiles ? c->nccl_tiles : d.tiles.p;
             uint32_t* gathered = c->nccl_gathered ? c->nccl_gathered : d.gathered.p;
             CU(d.frame.resize(npx));
-            CU(cudaEventRecord(d.ev0, st));
+            CU(cudaEventRecord(e0, st));
             rc = render_tiles(c, d, cam, p, rank, world, tiles, st, &launches); if (rc) return rc;
-            CU(cudaEventRecord(d.ev1, st));
+            CU(cudaEventRecord(e1, st));
             NC(g_nccl.AllGather(tiles, gathered, tile_px * 4, ncclUint8, c->comm, st));      // one per frame, equal (padded) counts: SURVEY §8(e)
             deinterleave_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, st>>>(gathered, p->width, p->height, tile_rows_of(p), world, tile_px, d.frame.p);
             CU(cudaGetLastError());
@@ -1108,6 +1124,13 @@ static int render_rank_impl(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_p
         CU(cudaMemcpyAsync(d.pinned, d_final, frame_bytes, cudaMemcpyDeviceToHost, st));
     }
     CU(cudaMemcpyAsync(d.pinned_cnt, d.counters.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    if (enqueue_only) {                                     // no host synchronisation: rtiow_ctx_synchronize collects the stats
+        ++d.ring_used;
+        d.enq_paths = (uint64_t)rows_of_rank(p->height, tile_rows_of(p), world, rank) * p->width * p->spp;
+        d.enq_launches += launches; d.enq_world = world;
+        if (d_frame_out) *d_frame_out = frame_here ? d_final : nullptr;
+        return RTIOW_OK;
+    }
     CU(cudaStreamSynchronize(st));
     if (out_rgba && frame_here) memcpy(out_rgba, d.pinned, frame_bytes);
     if (d_frame_out) *d_frame_out = frame_here ? d_final : nullptr;
@@ -1131,6 +1154,36 @@ extern "C" int rtiow_render_rank_device(rtiow_ctx* c, const rtiow_camera* cam, c
 {
     if (!d_frame) return fail(RTIOW_ERR_INVALID_ARG, "d_frame is NULL");
     return render_rank_impl(c, cam, p, nullptr, d_frame, stats);
+}
+
+// Frames back to back without a host round trip per frame (an animation, a bench's timed loop): the render kernel, the epilogue /
+// gather and the frame-complete barrier are enqueued on the ctx's stream and the call returns.
+extern "C" int rtiow_render_rank_enqueue(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_params* p, const void** d_frame)
+{
+    if (!d_frame) return fail(RTIOW_ERR_INVALID_ARG, "d_frame is NULL");
+    return render_rank_impl(c, cam, p, nullptr, d_frame, nullptr, true);
+}
+extern "C" int rtiow_ctx_synchronize(rtiow_ctx* c, rtiow_stats* stats)
+{
+    if (!c) return fail(RTIOW_ERR_INVALID_ARG, "ctx is NULL");
+    if (c->dev.size() != 1) return fail(RTIOW_ERR_INVALID_ARG, "rtiow_ctx_synchronize needs a one-device ctx (rtiow_ctx_create_rank)");
+    DeviceState& d = c->dev[0];
+    CU(cudaSetDevice(d.device));
+    CU(cudaStreamSynchronize(d.stream));
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        double sum = 0;
+        for (size_t i = 0; i < d.ring_used; ++i) { float ms = 0; CU(cudaEventElapsedTime(&ms, d.ring[i].first, d.ring[i].second)); sum += ms; }
+        if (d.ring_used) {
+            stats->kernel_ms = sum / (double)d.ring_used;            // mean over the frames enqueued since the last synchronize
+            stats->paths = d.enq_paths;                              // of the last frame, like rays_traced
+            stats->rays_traced = d.pinned_cnt[1]; stats->sphere_tests = stats->rays_traced * (uint64_t)d.scene.n;
+            stats->kernel_launches = d.enq_launches; stats->n_gpus = d.enq_world; stats->scan_backend = (uint32_t)d.last_backend;
+            stats->h2d_bytes = (sizeof(rtiow_camera) + sizeof(rtiow_params)) * d.ring_used; stats->d2h_bytes = 16 * d.ring_used;
+        }
+    }
+    d.ring_used = 0; d.enq_launches = 0;
+    return RTIOW_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

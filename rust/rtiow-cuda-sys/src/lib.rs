@@ -1,4 +1,4 @@
-//! Raw bindings to `include/rtiow_cuda.h` (ABI version 3).  One `extern "C"` item per exported symbol, one
+//! Raw bindings to `include/rtiow_cuda.h` (ABI version 4).  One `extern "C"` item per exported symbol, one
 //! `#[repr(C)]` struct per C struct; layouts are asserted in `tests/test_host_cabi.py::test_struct_layouts_match_header`
 //! (Camera 176 B, Params 48 B, Stats 72 B, Spheres/Materials 48 B).
 //!
@@ -7,7 +7,7 @@
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_int, c_void};
 
-pub const RTIOW_ABI_VERSION: c_int = 3;
+pub const RTIOW_ABI_VERSION: c_int = 4;
 
 pub const RTIOW_OK: c_int = 0;
 pub const RTIOW_ERR_INVALID_ARG: c_int = -1;
@@ -110,6 +110,8 @@ extern "C" {
     pub fn rtiow_render_rank(ctx: *mut rtiow_ctx, cam: *const rtiow_camera, p: *const rtiow_params, out_rgba: *mut u8, stats: *mut rtiow_stats) -> c_int;
     pub fn rtiow_render_rank_device(ctx: *mut rtiow_ctx, cam: *const rtiow_camera, p: *const rtiow_params, d_frame: *mut *const c_void,
                                     stats: *mut rtiow_stats) -> c_int;
+    pub fn rtiow_render_rank_enqueue(ctx: *mut rtiow_ctx, cam: *const rtiow_camera, p: *const rtiow_params, d_frame: *mut *const c_void) -> c_int;
+    pub fn rtiow_ctx_synchronize(ctx: *mut rtiow_ctx, stats: *mut rtiow_stats) -> c_int;
     pub fn rtiow_tile_buffer_bytes(p: *const rtiow_params, world: c_int, out_bytes: *mut usize) -> c_int;
     pub fn rtiow_render_tiles_device(ctx: *mut rtiow_ctx, cam: *const rtiow_camera, p: *const rtiow_params, rank: c_int, world: c_int,
                                      d_tiles: *mut c_void, stream: *mut c_void, stats: *mut rtiow_stats) -> c_int;

@@ -33,9 +33,9 @@ def test_rank_processes_gather_inside_the_library(capi, world):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
     assert res["nccl_identical_to_1gpu"] and res["auto_identical_to_1gpu"] and res["rank1_frame_identical"], res
-    assert "ncclAllGather" in res["nccl_note"]
+    assert "ncclAllGather" in res["nccl_note"] and res["enqueue_nccl_identical_to_1gpu"]
     if res.get("fused") != "unsupported":
-        assert res["fused_identical_to_1gpu"] and "rank 0's frame" in res["fused_note"], res
+        assert res["fused_identical_to_1gpu"] and res["enqueue_fused_identical_to_1gpu"] and "rank 0's frame" in res["fused_note"], res
 
 
 @pytest.mark.parametrize("n", [2, 4, 8])
@@ -66,3 +66,23 @@ def test_rank_ctx_world_1_needs_no_nccl(capi, final_scene):
         assert np.array_equal(a, b)
         ptr, st = rc.render_rank_device(cam, prm)
         assert ptr != 0 and st["n_gpus"] == 1
+
+
+def test_enqueued_frames_equal_the_synchronous_call(capi, final_scene):
+    """rtiow_render_rank_enqueue x K + rtiow_ctx_synchronize: frames back to back without a host round trip, same bytes, per-frame kernel times"""
+    _need(capi, 1)
+    W, H = 200, 113
+    cam = final_camera(capi, W / H)
+    with capi.Context(device=0, rank=0, world=1) as rc:
+        rc.upload_scene(**final_scene[0])
+        prms = [capi.default_params(width=W, height=H, spp=3, seed=s) for s in (5, 6, 7)]
+        refs = [rc.render_rank(cam, p)[0] for p in prms]
+        ptrs = [rc.render_rank_enqueue(cam, p) for p in prms]
+        st = rc.synchronize()
+        assert all(ptrs) and st["kernel_launches"] == 3 * 2 and st["kernel_ms"] > 0 and st["n_gpus"] == 1
+        last = capi.device_to_host(ptrs[-1], W * H * 4).reshape(H, W, 4)
+        assert np.array_equal(last, refs[-1])
+        assert st["rays_traced"] == rc.render_rank(cam, prms[-1])[1]["rays_traced"]
+        assert rc.synchronize()["kernel_launches"] == 0                      # nothing enqueued since
+        again, _ = rc.render_rank(cam, prms[0])
+        assert np.array_equal(again, refs[0])

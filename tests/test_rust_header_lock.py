@@ -85,7 +85,7 @@ def test_constants_match():
     consts = {m.group(1): int(m.group(2)) for m in re.finditer(r"\b(RTIOW_[A-Z0-9_]+)\s*=\s*(-?\d+)", h)}
     consts.update({m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+(RTIOW_[A-Z0-9_]+)\s+(-?\d+)", h)})
     rs = {m.group(1): int(m.group(2)) for m in re.finditer(r"pub const (RTIOW_[A-Z0-9_]+)\s*:\s*\w+\s*=\s*(-?\d+)\s*;", RS)}
-    assert consts["RTIOW_ABI_VERSION"] == rs["RTIOW_ABI_VERSION"] == 3
+    assert consts["RTIOW_ABI_VERSION"] == rs["RTIOW_ABI_VERSION"] == 4
     assert f"ABI version {consts['RTIOW_ABI_VERSION']}" in RS.splitlines()[0]
     missing = {k for k in consts if k not in rs and k != "RTIOW_CUDA_H"}
     assert not missing, f"constants of the header missing from lib.rs: {sorted(missing)}"
@@ -98,4 +98,4 @@ def test_ctypes_binding_and_library_export_the_same_symbols(capi):
     L = capi.lib()
     for name in c:
         assert hasattr(L, name), f"librtiow_cuda.so does not export {name}"
-    assert L.rtiow_abi_version() == 3
+    assert L.rtiow_abi_version() == 4

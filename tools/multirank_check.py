@@ -51,6 +51,16 @@ def rank_main(a):
             dt = (time.perf_counter() - t0) / a.bench
             if rank == 0:
                 res[name + "_ms_per_frame"] = dt * 1e3; res[name + "_mpaths_s"] = W * H * a.spp / dt / 1e6
+    # frames back to back without a host round trip (rtiow_render_rank_enqueue x 3 + rtiow_ctx_synchronize), both gathers
+    for name, mode in (("nccl", capi.GATHER_NCCL), ("fused", capi.GATHER_FUSED)):
+        if res.get(name) == "unsupported":
+            continue
+        ctx.set_gather(mode)
+        ptrs = [ctx.render_rank_enqueue(cam, prm) for _ in range(3)]
+        st = ctx.synchronize()
+        if rank == 0:
+            frames["enqueue_" + name] = capi.device_to_host(ptrs[-1], W * H * 4).reshape(H, W, 4)
+            res["enqueue_" + name + "_kernel_ms"] = st["kernel_ms"]
     if world > 1:                                    # NCCL gather with a host frame on every rank
         ctx.set_gather(capi.GATHER_NCCL)
         img_all, _ = ctx.render_rank(cam, prm, want_frame=True)
