@@ -72,8 +72,44 @@ unsafe extern "C" fn progress_trampoline(user: *mut std::os::raw::c_void, pass: 
     (p.f)(pass, n_passes, spp_done, std::slice::from_raw_parts(rgba, p.len)) as std::os::raw::c_int
 }
 
-fn render_impl(cam: &Camera, world: &HittableList, p: &RenderParams, n_passes: u32,
-               on_pass: Option<&mut dyn FnMut(u32, u32, u32, &[u8]) -> bool>) -> Result<Vec<u8>, RenderError> {
+/// One process per GPU (MPI ranks, one Rust process per device): rank 0 makes the id, hands its 128 bytes to the other ranks by
+/// any means, and every rank calls `render_rank` with the same camera, world and params.  The gather happens inside
+/// librtiow_cuda.so (one ncclAllGather per frame, or epilogue stores into rank 0's frame over NVLink): rank 0 gets
+/// `Some(pixels)`, the others `None`.  The frame is byte-identical to `render`'s on one GPU.
+pub fn nccl_unique_id() -> Result<[u8; 128], RenderError> {
+    let mut id = [0u8; 128];
+    let rc = unsafe { sys::rtiow_nccl_unique_id(id.as_mut_ptr() as *mut std::os::raw::c_void) };
+    if rc != sys::RTIOW_OK { return Err(err(rc)); }
+    Ok(id)
+}
+
+pub fn render_rank(cam: &Camera, world: &HittableList, p: &RenderParams, device: i32, rank: i32, ranks: i32,
+                   nccl_id: &[u8; 128]) -> Result<Option<Vec<u8>>, RenderError> {
+    unsafe {
+        let mut raw: *mut sys::rtiow_ctx = ptr::null_mut();
+        let rc = sys::rtiow_ctx_create_rank(device, rank, ranks, nccl_id.as_ptr() as *const std::os::raw::c_void, &mut raw);
+        if rc != sys::RTIOW_OK { return Err(err(rc)); }
+        let ctx = Ctx(raw);
+        upload(&ctx, world)?;
+        let prm = raw_params(p);
+        let mut pixels = if rank == 0 { vec![0u8; 4 * p.width as usize * p.height as usize] } else { vec![] };
+        let out = if rank == 0 { pixels.as_mut_ptr() } else { ptr::null_mut() };
+        let rc = sys::rtiow_render_rank(ctx.0, &cam.raw(), &prm, out, ptr::null_mut());
+        if rc != sys::RTIOW_OK { return Err(err(rc)); }
+        Ok(if rank == 0 { Some(pixels) } else { None })
+    }
+}
+
+unsafe fn raw_params(p: &RenderParams) -> sys::rtiow_params {
+    let mut prm: sys::rtiow_params = std::mem::zeroed();
+    sys::rtiow_params_default(&mut prm);
+    prm.width = p.width; prm.height = p.height; prm.spp = p.spp; prm.max_depth = p.max_depth; prm.t_min = p.t_min;
+    prm.seed = p.seed; prm.alpha = p.alpha;
+    prm
+}
+
+/// `&world` (main.rs:62-99) -> SoA arrays -> rtiow_scene_upload
+unsafe fn upload(ctx: &Ctx, world: &HittableList) -> Result<(), RenderError> {
     // flatten the trait objects through the provided describe() methods; unknown ones are an error, not a CPU fallback
     let (mut cx, mut cy, mut cz, mut radius, mut mat_index) = (vec![], vec![], vec![], vec![], vec![]);
     let (mut kind, mut ar, mut ag, mut ab, mut param) = (vec![], vec![], vec![], vec![], vec![]);
@@ -88,19 +124,24 @@ fn render_impl(cam: &Camera, world: &HittableList, p: &RenderParams, n_passes: u
         };
         cx.push(s.center[0]); cy.push(s.center[1]); cz.push(s.center[2]); radius.push(s.radius); mat_index.push(id as u32);
     }
+    {
+        let spheres = sys::rtiow_spheres { cx: cx.as_ptr(), cy: cy.as_ptr(), cz: cz.as_ptr(), radius: radius.as_ptr(), mat_index: mat_index.as_ptr(), n: radius.len() as u32 };
+        let mats = sys::rtiow_materials { kind: kind.as_ptr(), albedo_r: ar.as_ptr(), albedo_g: ag.as_ptr(), albedo_b: ab.as_ptr(), param: param.as_ptr(), n: kind.len() as u32 };
+        let rc = sys::rtiow_scene_upload(ctx.0, &spheres, &mats);
+        if rc != sys::RTIOW_OK { return Err(err(rc)); }
+        Ok(())
+    }
+}
+
+fn render_impl(cam: &Camera, world: &HittableList, p: &RenderParams, n_passes: u32,
+               on_pass: Option<&mut dyn FnMut(u32, u32, u32, &[u8]) -> bool>) -> Result<Vec<u8>, RenderError> {
     unsafe {
         let mut raw: *mut sys::rtiow_ctx = ptr::null_mut();
         let rc = sys::rtiow_ctx_create(p.n_gpus, &mut raw);
         if rc != sys::RTIOW_OK { return Err(err(rc)); }
         let ctx = Ctx(raw);
-        let spheres = sys::rtiow_spheres { cx: cx.as_ptr(), cy: cy.as_ptr(), cz: cz.as_ptr(), radius: radius.as_ptr(), mat_index: mat_index.as_ptr(), n: radius.len() as u32 };
-        let mats = sys::rtiow_materials { kind: kind.as_ptr(), albedo_r: ar.as_ptr(), albedo_g: ag.as_ptr(), albedo_b: ab.as_ptr(), param: param.as_ptr(), n: kind.len() as u32 };
-        let rc = sys::rtiow_scene_upload(ctx.0, &spheres, &mats);
-        if rc != sys::RTIOW_OK { return Err(err(rc)); }
-        let mut prm: sys::rtiow_params = std::mem::zeroed();
-        sys::rtiow_params_default(&mut prm);
-        prm.width = p.width; prm.height = p.height; prm.spp = p.spp; prm.max_depth = p.max_depth; prm.t_min = p.t_min;
-        prm.seed = p.seed; prm.alpha = p.alpha;
+        upload(&ctx, world)?;
+        let prm = raw_params(p);
         let mut pixels = vec![0u8; 4 * p.width as usize * p.height as usize];
         let rc = match on_pass {
             None if n_passes == 0 => sys::rtiow_render(ctx.0, &cam.raw(), &prm, pixels.as_mut_ptr(), ptr::null_mut()),
