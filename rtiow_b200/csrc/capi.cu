@@ -670,7 +670,7 @@ static int launch_render(const rtiow_ctx* c, DeviceState& d, const rtiow_camera*
             CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
             grid = d.sms;
             size_fetch(a, grid, Shape::kRayThreads);
-            k<<<grid, Shape::kThreads, sm, st>>>(a);
+            k<<<grid, Shape::kRenderThreads, sm, st>>>(a);
             d.last_backend = RTIOW_SCAN_TENSOR;
         }
     } else {

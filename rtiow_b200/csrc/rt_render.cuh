@@ -304,15 +304,19 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) render_kernel(const Render
 // filter moves from 7 FFMA2 per sphere pair to three tcgen05.mma per 128 rays x NC spheres, and the warp-level "any lane
 // alive" vote becomes a 128-thread one, because a group's 128 rays form one MMA.
 template <int G, int NC>
-__global__ void __launch_bounds__(G * 160, 1) render_kernel_umma(const RenderArgs<float> a)
+__global__ void __launch_bounds__(UmmaShape<G, NC>::kRenderThreads, 1) render_kernel_umma(const RenderArgs<float> a)
 {
     extern __shared__ __align__(1024) unsigned char smem_umma[];
     uint32_t tmem_base;
     UmmaCtx ux = umma_setup<G, NC>(smem_umma, a.scene, &tmem_base);
     const unsigned lane = threadIdx.x & 31u;
     if (ux.issuer_warp) {
-        umma_issuer<G, NC>(ux);
+        // the issuer warps (and the warps that pad them to whole warpgroups) give registers back, the ray warps take them:
+        // 1024 threads x 64 registers is the whole file; 8 warps down to 32 frees 8 K, 24 ray warps up to 72 take 6 K
+        umma::setmaxnreg_dec<RT_UMMA_ISSUER_REGS>();
+        if ((threadIdx.x >> 5) < 5 * G) umma_issuer<G, NC>(ux);
     } else {
+        umma::setmaxnreg_inc<RT_UMMA_RAY_REGS>();
         const unsigned lt_mask = (1u << lane) - 1u;
         PathState<float> ps; init_path(ps);
         uint32_t acc_lp = 0;

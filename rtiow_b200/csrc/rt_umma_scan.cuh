@@ -38,11 +38,19 @@ namespace rt {
 #ifndef RT_UMMA_EMPTY_NAMED
 #define RT_UMMA_EMPTY_NAMED 1                 // "D has been read": a named barrier (bar.arrive / bar.sync) instead of an mbarrier the issuer polls
 #endif
+#ifndef RT_UMMA_RAY_REGS
+#define RT_UMMA_RAY_REGS 72                   // setmaxnreg of the render kernel's ray warpgroups ...
+#define RT_UMMA_ISSUER_REGS 32                // ... and of its issuer warpgroups (launch bound: 64)
+#endif
 #define RT_UMMA_MIN_SMEM (120 * 1024)        // > half an SM's shared memory: one CTA per SM (each CTA allocates all of TMEM)
 
 template <int G, int NC> struct UmmaShape {
     static_assert(NC % 32 == 0 && NC >= 32 && NC <= 256, "chunk = whole 32-sphere words");
     static constexpr int kRayThreads = G * 128, kThreads = G * 160;
+    // the render kernel re-balances registers between its ray warps and its issuer warps (setmaxnreg works on whole warpgroups of
+    // 128 threads), so it is launched with the issuer side padded to a whole warpgroup; the padding warps only take part in the
+    // set-up and tear-down barriers
+    static constexpr int kRenderThreads = (kThreads + 127) / 128 * 128;
     static constexpr int kCols = NC + 16;                        // TMEM columns per group: D (NC) + A_hi (8) + A_lo (8)
     static_assert(G * kCols <= 512, "TMEM has 512 columns");
     static_assert(G <= 6, "named barriers: 0 = __syncthreads, 1..G the groups' votes, 7..6+G their hand-back barriers");
@@ -93,7 +101,7 @@ __device__ __forceinline__ UmmaCtx umma_setup(unsigned char* smem_raw, const Sce
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + S::bars_offset_bytes(sc.u_npad));       // [G][8]: a_full, full, empty
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + G * 8);
     int* quit = reinterpret_cast<int*>(tmem_slot + 4);
-    for (size_t i = (size_t)tid * 16; i < 2 * blk; i += (size_t)S::kThreads * 16)
+    for (size_t i = (size_t)tid * 16; i < 2 * blk; i += (size_t)blockDim.x * 16)
         *reinterpret_cast<uint4*>(b_img + i) = *reinterpret_cast<const uint4*>(sc.u_bimg + i);
     if (tid == 0) {
         for (int i = 0; i < G; ++i) {
