@@ -177,7 +177,8 @@ int rtiow_render_rank_device(rtiow_ctx* ctx, const rtiow_camera* cam, const rtio
  * there): rtiow_render_rank_device WITHOUT the host synchronisation — kernel, epilogue / gather and the frame-complete barrier are
  * enqueued on the ctx's stream and the call returns.  *d_frame as above; with the FUSED gather two frame buffers alternate, so a
  * frame stays valid until the second-next enqueue.  rtiow_ctx_synchronize waits for everything enqueued; its stats (may be NULL)
- * carry the MEAN kernel_ms of the frames enqueued since the last synchronize and the paths / rays of the last one. */
+ * carry the MEAN kernel_ms of the frames enqueued since the last synchronize and the paths / rays of the last one.  At most 1024
+ * frames may be enqueued between two synchronizes (one event pair each). */
 int rtiow_render_rank_enqueue(rtiow_ctx* ctx, const rtiow_camera* cam, const rtiow_params* p, const void** d_frame);
 int rtiow_ctx_synchronize(rtiow_ctx* ctx, rtiow_stats* stats);
 

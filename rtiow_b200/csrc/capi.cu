@@ -1060,6 +1060,7 @@ static int render_rank_impl(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_p
     // the events around the render kernel: the ctx's pair, or — for a frame that is only enqueued — the next pair of the ring
     cudaEvent_t e0 = d.ev0, e1 = d.ev1;
     if (enqueue_only) {
+        if (d.ring_used >= 1024) return fail(RTIOW_ERR_INVALID_ARG, "1024 frames enqueued: call rtiow_ctx_synchronize before enqueuing more");
         if (d.ring_used == d.ring.size()) {
             std::pair<cudaEvent_t, cudaEvent_t> ev{ nullptr, nullptr };
             CU(cudaEventCreate(&ev.first)); CU(cudaEventCreate(&ev.second));
