@@ -42,6 +42,9 @@ namespace rt {
 #define RT_UMMA_RAY_REGS 72                   // setmaxnreg of the render kernel's ray warpgroups ...
 #define RT_UMMA_ISSUER_REGS 32                // ... and of its issuer warpgroups (launch bound: 64)
 #endif
+#ifndef RT_UMMA_DRAIN_ILP
+#define RT_UMMA_DRAIN_ILP 3                   // survivors per lane per lock-step round of the precise test (2: -0.2 %, 4: -0.4 %)
+#endif
 #define RT_UMMA_MIN_SMEM (120 * 1024)        // > half an SM's shared memory: one CTA per SM (each CTA allocates all of TMEM)
 
 template <int G, int NC> struct UmmaShape {
@@ -299,16 +302,23 @@ __device__ __forceinline__ HitF closest_hit_umma(UmmaCtx& ux, const SceneDev& sc
         RT_STAMP(70 + c);
     }
     RT_STAMP(7);
-    // survivors through the precise test, the warp in lock step, TWO per round: the test is one dependent chain (load, ~25 FP
-    // operations, a MUFU), so two independent ones per lane halve the rounds' latency (the drain was 11 % of an iteration)
+    // survivors through the precise test, the warp in lock step, RT_UMMA_DRAIN_ILP per round: the test is one dependent chain (load,
+    // ~25 FP operations, a MUFU), so independent ones per lane divide the rounds' latency (the drain is 11 % of an iteration); all of
+    // a round's list reads and sphere loads are issued before its first test (that alone was worth 2 %)
     const int nmax = __reduce_max_sync(RT_FULL, nc);
-    for (int k = 0; k < nmax; k += 2) {
-        const bool h0 = k < nc, h1 = k + 1 < nc;
-        const int p0 = h0 ? ux.cand[k * kStride] : self_code, p1 = h1 ? ux.cand[(k + 1) * kStride] : self_code;
-        const bool g0 = h0 && p0 != self_code, g1 = h1 && p1 != self_code;
-        const float4 s0 = g0 ? sc.small[p0] : make_float4(0.f, 0.f, 0.f, 0.f), s1 = g1 ? sc.small[p1] : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (g0) candidate<float, true>(o, dhat, inv_a, t_min, mk(s0.x, s0.y, s0.z), s0.w, p0, &tb, &pb);
-        if (g1) candidate<float, true>(o, dhat, inv_a, t_min, mk(s1.x, s1.y, s1.z), s1.w, p1, &tb, &pb);
+    for (int k = 0; k < nmax; k += RT_UMMA_DRAIN_ILP) {
+        int pp[RT_UMMA_DRAIN_ILP]; bool gg[RT_UMMA_DRAIN_ILP]; float4 ss[RT_UMMA_DRAIN_ILP];
+#pragma unroll
+        for (int j = 0; j < RT_UMMA_DRAIN_ILP; ++j) {
+            const bool h = k + j < nc;
+            pp[j] = h ? ux.cand[(k + j) * kStride] : self_code;
+            gg[j] = h && pp[j] != self_code;
+        }
+#pragma unroll
+        for (int j = 0; j < RT_UMMA_DRAIN_ILP; ++j) ss[j] = gg[j] ? sc.small[pp[j]] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < RT_UMMA_DRAIN_ILP; ++j)
+            if (gg[j]) candidate<float, true>(o, dhat, inv_a, t_min, mk(ss[j].x, ss[j].y, ss[j].z), ss[j].w, pp[j], &tb, &pb);
     }
     RT_STAMP(8);
     HitF h; h.t = tb; h.idx = pb >= 0 ? sc.small_idx[pb] : -1; h.code = pb;
