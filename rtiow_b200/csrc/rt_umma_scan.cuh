@@ -2,19 +2,20 @@
 //
 // CTA = G ray groups of 128 threads (4 warps: warp q of a group owns TMEM lanes [32q, 32q+32)) + G issuer warps.
 // One scan of a group = 128 rays against every small sphere of the scene:
-//   ray threads   : feature rows of the ray (rt_umma.cuh) -> tcgen05.st into the group's A columns -> arrive(a_full)
-//   issuer thread : wait(a_full); per chunk of NC spheres: wait(empty) ; 3 x tcgen05.mma (hi.hi + hi.lo + lo.hi) into the
-//                   group's D columns ; tcgen05.commit -> full
-//   ray threads   : wait(full) ; tcgen05.ld their own lane: NC discriminants of THEIR ray ; arrive(empty) ; funnel-shift
-//                   the sign bits into 32-sphere words ; survivors -> per-lane candidate list -> precise test
-//                   (sphere_roots, rt_device.cuh), exactly as the FP32 scan of rt_scene.cuh does.
+//   ray threads   : the ray's two rows (rt_umma.cuh, ray_rows) -> tcgen05.st into the group's A columns -> arrive(a_full, mbarrier)
+//   issuer warp   : wait(a_full); per chunk of NC spheres: bar.sync(hand-back) ; 2 x tcgen05.mma (row2 . B2, then row1 . B1) into
+//                   the group's D columns (fp16 accumulator) ; tcgen05.commit -> full (mbarrier)
+//   ray threads   : wait(full) ; tcgen05.ld.pack::16b their own lane: NC discriminants of THEIR ray, two per register ;
+//                   bar.arrive(hand-back) ; sign bits -> 32-sphere words, four per instruction (sign_word16) ; survivors ->
+//                   per-lane candidate list -> precise test (sphere_roots, rt_device.cuh), exactly as the FP32 scan of
+//                   rt_scene.cuh does.
 // The issuer is a warp of its own because tcgen05.mma issue stalls the issuing thread while the tensor pipe is busy
 // (tools/probe_umma_filter.cu: an issuer that shares a warp with an epilogue halves the throughput), and every group has
 // its own: one thread polling all groups' barriers (mbarrier.test_wait) measured 40 % slower in situ.  D is single-buffered
 // per group: while one group's MMAs run, the other groups collect signs, so the tensor pipe and the ALU pipe overlap across
-// groups (stand-alone, G = 4, NC = 64: 143.6 TFLOP/s-equivalent against 65.8 for the FP32 filter).  The render kernel is
-// bound by the latency of its per-ray code, and every extra group hides more of it (G = 4 -> 6: +13 %), so G is as large
-// as TMEM allows: 6 x (64 + 16) = 480 of 512 columns.
+// groups.  The render kernel is bound by latency chains — the per-chunk round trip and the per-ray code — and every extra group
+// hides more of them (G = 4 -> 6: +13 %), so G is as large as TMEM allows: 6 x (64 + 16) = 480 of 512 columns (what was
+// measured around this shape is in DESIGN.md §1.2 and §7.1).
 // Each CTA owns all 512 TMEM columns, so exactly one CTA may live on an SM: the launch asks for more than half of the
 // SM's shared memory.
 #pragma once
@@ -24,7 +25,7 @@
 namespace rt {
 
 #ifndef RT_UMMA_GROUPS
-#define RT_UMMA_GROUPS 6                      // ray groups per CTA in the product kernels (24 ray warps + 6 issuer warps = 960 threads, 64 registers)
+#define RT_UMMA_GROUPS 6                      // ray groups per CTA in the product kernels (24 ray warps + 6 issuer warps = 960 threads; the render kernel pads to 1024)
 #endif
 #ifndef RT_UMMA_CHUNK
 #define RT_UMMA_CHUNK 64                      // spheres per MMA chunk (TMEM: 6 x (64 + 16) = 480 of 512 columns)
@@ -34,9 +35,6 @@ namespace rt {
 #endif
 #ifndef RT_UMMA_D16
 #define RT_UMMA_D16 1                         // fp16 accumulator + packed sign collection (rt_umma.cuh, sign_word16); the only form left
-#endif
-#ifndef RT_UMMA_EMPTY_NAMED
-#define RT_UMMA_EMPTY_NAMED 1                 // "D has been read": a named barrier (bar.arrive / bar.sync) instead of an mbarrier the issuer polls
 #endif
 #ifndef RT_UMMA_RAY_REGS
 #define RT_UMMA_RAY_REGS 72                   // setmaxnreg of the render kernel's ray warpgroups ...
@@ -54,7 +52,7 @@ template <int G, int NC> struct UmmaShape {
     // 128 threads), so it is launched with the issuer side padded to a whole warpgroup; the padding warps only take part in the
     // set-up and tear-down barriers
     static constexpr int kRenderThreads = (kThreads + 127) / 128 * 128;
-    static constexpr int kCols = NC + 16;                        // TMEM columns per group: D (NC) + A_hi (8) + A_lo (8)
+    static constexpr int kCols = NC + 16;                        // TMEM columns per group: D (NC) + the rays' row1 (8) + row2 (8)
     static_assert(G * kCols <= 512, "TMEM has 512 columns");
     static_assert(G <= 6, "named barriers: 0 = __syncthreads, 1..G the groups' votes, 7..6+G their hand-back barriers");
     static constexpr size_t kCandBytes = (size_t)kRayThreads * RT_CAND_CAP * sizeof(uint16_t);
@@ -80,9 +78,9 @@ __device__ int g_umma_trace_n;
 
 // per-thread view of its group's resources
 struct UmmaCtx {
-    uint32_t t_d, t_a;              // TMEM columns of the group's D and A (A_hi at t_a, A_lo at t_a + 8); lane field 0
+    uint32_t t_d, t_a;              // TMEM columns of the group's D and A (row1 at t_a, row2 at t_a + 8); lane field 0
     uint32_t lane_base;             // this warp's TMEM lane quarter, in the address's lane field
-    uint32_t bar_afull, bar_full, bar_empty;
+    uint32_t bar_afull, bar_full;   // mbarriers: the group's 128 rows are in TMEM / the chunk's MMAs have completed (tcgen05.commit)
     uint32_t s_hi, s_lo;            // shared-window addresses of the B image's two K blocks
     uint32_t full_phase;            // parity of the next phase of `full` to wait for
     int n_chunks;
@@ -101,7 +99,7 @@ __device__ __forceinline__ UmmaCtx umma_setup(unsigned char* smem_raw, const Sce
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     unsigned char* b_img = smem_raw + S::b_offset_bytes();
     const size_t blk = RT_UMMA_B_BLOCK_BYTES(sc.u_npad);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + S::bars_offset_bytes(sc.u_npad));       // [G][8]: a_full, full, empty
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + S::bars_offset_bytes(sc.u_npad));       // [G][8]: a_full, full
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + G * 8);
     int* quit = reinterpret_cast<int*>(tmem_slot + 4);
     for (size_t i = (size_t)tid * 16; i < 2 * blk; i += (size_t)blockDim.x * 16)
@@ -110,7 +108,6 @@ __device__ __forceinline__ UmmaCtx umma_setup(unsigned char* smem_raw, const Sce
         for (int i = 0; i < G; ++i) {
             mbar_init(smem_u32(bars + 8 * i + 0), 128);       // every ray thread of the group
             mbar_init(smem_u32(bars + 8 * i + 1), 1);         // tcgen05.commit
-            mbar_init(smem_u32(bars + 8 * i + 2), 4);         // lane 0 of the group's four warps
             quit[i] = 0;
         }
         fence_mbar_init();
@@ -131,7 +128,7 @@ __device__ __forceinline__ UmmaCtx umma_setup(unsigned char* smem_raw, const Sce
     ux.t_d = tmem_base + (uint32_t)(ux.group * S::kCols);
     ux.t_a = ux.t_d + NC;
     ux.lane_base = (uint32_t)(32 * (warp & 3)) << 16;
-    ux.bar_afull = smem_u32(bars + 8 * ux.group); ux.bar_full = ux.bar_afull + 8; ux.bar_empty = ux.bar_afull + 16;
+    ux.bar_afull = smem_u32(bars + 8 * ux.group); ux.bar_full = ux.bar_afull + 8;
     ux.s_hi = smem_u32(b_img); ux.s_lo = ux.s_hi + (uint32_t)blk;
     ux.full_phase = 0;
     ux.n_chunks = sc.u_npad / NC;
@@ -140,7 +137,7 @@ __device__ __forceinline__ UmmaCtx umma_setup(unsigned char* smem_raw, const Sce
     // every one of these is the same in all lanes of a warp; broadcasting them from lane 0 tells the compiler so, and it keeps
     // TMEM addresses and barrier addresses in uniform registers (LDTM / STTM / SYNCS take them from there)
     ux.t_d = __shfl_sync(RT_FULL, ux.t_d, 0); ux.t_a = __shfl_sync(RT_FULL, ux.t_a, 0); ux.lane_base = __shfl_sync(RT_FULL, ux.lane_base, 0);
-    ux.bar_afull = __shfl_sync(RT_FULL, ux.bar_afull, 0); ux.bar_full = ux.bar_afull + 8; ux.bar_empty = ux.bar_afull + 16;
+    ux.bar_afull = __shfl_sync(RT_FULL, ux.bar_afull, 0); ux.bar_full = ux.bar_afull + 8;
     ux.n_chunks = __shfl_sync(RT_FULL, ux.n_chunks, 0);
     return ux;
 }
@@ -155,14 +152,14 @@ __device__ __forceinline__ void umma_issuer(const UmmaCtx& ux)
 {
     using namespace umma;
     const uint32_t t_d = __shfl_sync(RT_FULL, ux.t_d, 0), t_a = __shfl_sync(RT_FULL, ux.t_a, 0);
-    const uint32_t bar_afull = __shfl_sync(RT_FULL, ux.bar_afull, 0), bar_full = bar_afull + 8u, bar_empty = bar_afull + 16u;
+    const uint32_t bar_afull = __shfl_sync(RT_FULL, ux.bar_afull, 0), bar_full = bar_afull + 8u;
     const uint32_t s_hi = __shfl_sync(RT_FULL, ux.s_hi, 0), s_lo = __shfl_sync(RT_FULL, ux.s_lo, 0);
     const int n_chunks = __shfl_sync(RT_FULL, ux.n_chunks, 0);
     const int group = __shfl_sync(RT_FULL, ux.group, 0);
     const uint32_t idesc = make_idesc_f16_f16(NC);
     const uint64_t dh0 = make_smem_desc(s_hi, RT_UMMA_B_LBO, RT_UMMA_B_SBO), dl0 = make_smem_desc(s_lo, RT_UMMA_B_LBO, RT_UMMA_B_SBO);
     constexpr uint32_t kStep = ((uint32_t)(NC / 8) * RT_UMMA_B_SBO) >> 4;     // descriptor start-address units (16 bytes) per chunk
-    uint32_t a_phase = 0, e_phase = 0; bool used = false;
+    uint32_t a_phase = 0; bool used = false;
     for (;;) {
         mbar_wait(bar_afull, a_phase, RT_UMMA_AFULL_BACKOFF_NS); a_phase ^= 1u;   // all 128 feature rows are in TMEM — or the group is done
         if (*ux.quit) break;
@@ -170,11 +167,7 @@ __device__ __forceinline__ void umma_issuer(const UmmaCtx& ux)
         uint64_t dh = dh0, dl = dl0;                                           // the chunk's B descriptors, stepped after the issue so that
 #pragma unroll 1                                                               // nothing but the MMAs stands between the barrier and the tensor pipe
         for (int c = 0; c < n_chunks; ++c) {
-#if RT_UMMA_EMPTY_NAMED
-            if (used) { named_bar_sync(7 + group, 160); tc_fence_after(); }                       // the previous chunk's D has been read
-#else
-            if (used) { mbar_wait(bar_empty, e_phase); e_phase ^= 1u; tc_fence_after(); }         // the previous chunk's D has been read
-#endif
+            if (used) { named_bar_sync(7 + group, 160); tc_fence_after(); }       // the previous chunk's D has been read (umma_hand_back)
             used = true;
             if (elect_one()) {
                 mma_f16_ts(t_d, t_a + 8u, dl, idesc, 0u);                 // row2 . B2: the cross terms (small: the fp16 rounding of the
@@ -209,12 +202,7 @@ __device__ __forceinline__ void umma_teardown(uint32_t tmem_base)
 // path (ray rows -> MMA -> commit -> TMEM load -> hand back -> MMA ...: ~900 cycles per chunk for ~90 cycles of tensor work)
 __device__ __forceinline__ void umma_hand_back(const UmmaCtx& ux)
 {
-#if RT_UMMA_EMPTY_NAMED
     umma::named_bar_arrive(7 + ux.group, 160);
-#else
-    __syncwarp();
-    if ((threadIdx.x & 31) == 0) umma::mbar_arrive(ux.bar_empty);
-#endif
 }
 
 // Closest hit of one ray against the whole scene — the tensor-core twin of closest_hit<kSmem> (rt_scene.cuh); every one of
