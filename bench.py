@@ -264,7 +264,7 @@ def run_ours(args, rank, local_rank, world):
     stream = torch.cuda.Stream(dev)
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
-    host_np = np.empty((H, W, 4), np.uint8)
+    host_np = torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True).numpy()       # page-locked: the library DMAs the frame straight into it
 
     def step_device():
         """this rank's rows + the gather, frame left in HBM (rank 0)"""

@@ -71,6 +71,8 @@ template <typename U> struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
 };
 
+template <typename U> struct DevPtr { unsigned char* raw; U* p() const { return reinterpret_cast<U*>(raw); } };   // a typed view into the scene blob
+
 struct DeviceState {
     int device = 0;
     int sms = 0;
@@ -80,10 +82,9 @@ struct DeviceState {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ring; size_t ring_used = 0;
     uint64_t enq_paths = 0; uint32_t enq_launches = 0; uint32_t enq_world = 1;
     // scene
-    DevBuf<float> table; DevBuf<float4> small; DevBuf<int> small_idx; DevBuf<double4> big; DevBuf<int> big_idx;
-    DevBuf<float4> sph; DevBuf<double4> sphd; DevBuf<float4> mat; DevBuf<double4> matd; DevBuf<uint8_t> kind;
-    DevBuf<float4> bigf;                               // large spheres, f32 fast path (rt_scene.cuh big_spheres_f32)
-    DevBuf<unsigned char> ubimg;                       // tensor-core filter: the spheres' fp16 hi/lo feature image (rt_umma.cuh)
+    // every scene array lives in ONE device allocation, filled by ONE H2D copy from a page-locked staging blob (rtiow_scene_upload):
+    // twelve small pageable copies cost 0.25 ms per upload, which is 2.5 % of a 10 ms frame in the end-to-end call at 8 GPUs
+    DevBuf<unsigned char> scene_blob;
     SceneDev scene{};
     bool has_scene = false;
     // frame
@@ -100,6 +101,7 @@ struct rtiow_ctx {
     std::vector<DeviceState> dev;
     int scan_backend = RTIOW_SCAN_AUTO;  // rtiow_ctx_set_scan_backend
     size_t scene_bytes = 0;
+    unsigned char* scene_stage = nullptr; size_t scene_stage_bytes = 0;   // page-locked staging blob of rtiow_scene_upload
     bool peer_ok = true;                 // every device can store into device 0's memory (NVLink P2P): fused epilogue + gather
     // the gather of the row tiles (rtiow_ctx_set_gather)
     int gather = RTIOW_GATHER_AUTO;
@@ -116,6 +118,15 @@ struct rtiow_ctx {
     bool windows_registered = false;
     std::string gather_note;
 };
+
+// is this host pointer page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory)?  Then a D2H copy can DMA straight into it.
+static bool host_is_pinned(const void* p)
+{
+    cudaPointerAttributes pa{};
+    const bool yes = cudaPointerGetAttributes(&pa, p) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    (void)cudaGetLastError();
+    return yes;
+}
 
 static int init_device(DeviceState& d, int device)
 {
@@ -320,8 +331,7 @@ extern "C" void rtiow_ctx_destroy(rtiow_ctx* c)
     for (auto& d : c->dev) {
         cudaSetDevice(d.device);
         if (d.stream) cudaStreamSynchronize(d.stream);
-        d.table.release(); d.small.release(); d.small_idx.release(); d.big.release(); d.big_idx.release();
-        d.sph.release(); d.sphd.release(); d.mat.release(); d.matd.release(); d.kind.release(); d.ubimg.release(); d.bigf.release();
+        d.scene_blob.release();
         d.accum.release(); d.counters.release(); d.tiles.release(); d.gathered.release(); d.frame.release();
         d.flush.release(); d.probe.release();
         if (d.pinned) cudaFreeHost(d.pinned);
@@ -332,6 +342,7 @@ extern "C" void rtiow_ctx_destroy(rtiow_ctx* c)
         for (auto& ev : d.ring) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
         if (d.stream && d.owns_stream) cudaStreamDestroy(d.stream);
     }
+    if (c->scene_stage) cudaFreeHost(c->scene_stage);
     delete c;
 }
 
@@ -464,24 +475,39 @@ extern "C" int rtiow_scene_upload(rtiow_ctx* c, const rtiow_spheres* s, const rt
             }
         }
     }
+    // layout of the blob: every array at a 256-byte boundary
+    struct Part { const void* src; size_t bytes, off; };
+    Part parts[12] = {
+        { table.data(), table.size() * sizeof(float), 0 }, { small.data(), (size_t)np * sizeof(float4), 0 }, { small_idx.data(), (size_t)np * sizeof(int), 0 },
+        { big.data(), (size_t)nb * sizeof(double4), 0 }, { big_ids.data(), (size_t)nb * sizeof(int), 0 },
+        { sph.data(), (size_t)n * sizeof(float4), 0 }, { sphd.data(), (size_t)n * sizeof(double4), 0 }, { mat.data(), (size_t)n * sizeof(float4), 0 },
+        { matd.data(), (size_t)n * sizeof(double4), 0 }, { kind.data(), (size_t)n * sizeof(uint8_t), 0 },
+        { ubimg.data(), ubimg.size(), 0 }, { bigf.data(), bigf.size() * sizeof(float4), 0 } };
+    size_t blob_bytes = 0, payload = 0;
+    for (auto& pt : parts) { pt.off = blob_bytes; blob_bytes += (pt.bytes + 255) & ~(size_t)255; payload += pt.bytes; }
+    if (c->scene_stage_bytes < blob_bytes) {
+        if (c->scene_stage) cudaFreeHost(c->scene_stage);
+        c->scene_stage = nullptr; c->scene_stage_bytes = 0;
+        CU(cudaMallocHost(&c->scene_stage, blob_bytes)); c->scene_stage_bytes = blob_bytes;
+    }
+    for (auto& pt : parts) if (pt.bytes) memcpy(c->scene_stage + pt.off, pt.src, pt.bytes);
     c->scene_bytes = 0;
     for (auto& d : c->dev) {
         CU(cudaSetDevice(d.device));
-        CU(d.table.resize(table.size())); CU(d.small.resize(np)); CU(d.small_idx.resize(np)); CU(d.big.resize(nb)); CU(d.big_idx.resize(nb));
-        CU(d.sph.resize(n)); CU(d.sphd.resize(n)); CU(d.mat.resize(n)); CU(d.matd.resize(n)); CU(d.kind.resize(n)); CU(d.ubimg.resize(ubimg.size())); CU(d.bigf.resize(bigf.size()));
-        size_t bytes = 0;
-#define UP(dst, src, cnt, type) do { if ((cnt) > 0) { CU(cudaMemcpyAsync(dst.p, src.data(), (size_t)(cnt) * sizeof(type), cudaMemcpyHostToDevice, d.stream)); bytes += (size_t)(cnt) * sizeof(type); } } while (0)
-        UP(d.table, table, table.size(), float); UP(d.small, small, np, float4); UP(d.small_idx, small_idx, np, int);
-        UP(d.big, big, nb, double4); UP(d.big_idx, big_ids, nb, int);
-        UP(d.sph, sph, n, float4); UP(d.sphd, sphd, n, double4); UP(d.mat, mat, n, float4); UP(d.matd, matd, n, double4); UP(d.kind, kind, n, uint8_t);
-        UP(d.ubimg, ubimg, ubimg.size(), unsigned char); UP(d.bigf, bigf, bigf.size(), float4);
-#undef UP
+        CU(d.scene_blob.resize(blob_bytes));
+        CU(cudaMemcpyAsync(d.scene_blob.p, c->scene_stage, blob_bytes, cudaMemcpyHostToDevice, d.stream));
         CU(cudaStreamSynchronize(d.stream));
-        d.scene.table = d.table.p; d.scene.small = d.small.p; d.scene.small_idx = d.small_idx.p; d.scene.np = np; d.scene.n_rec = (ns + 3) / 4;
+        const size_t bytes = payload;
+        unsigned char* B = d.scene_blob.p;
+        struct { DevPtr<float> table; DevPtr<float4> small; DevPtr<int> small_idx; DevPtr<double4> big; DevPtr<int> big_idx; DevPtr<float4> sph; DevPtr<double4> sphd;
+                 DevPtr<float4> mat; DevPtr<double4> matd; DevPtr<uint8_t> kind; DevPtr<unsigned char> ubimg; DevPtr<float4> bigf; } dd = {
+            { B + parts[0].off }, { B + parts[1].off }, { B + parts[2].off }, { B + parts[3].off }, { B + parts[4].off }, { B + parts[5].off }, { B + parts[6].off },
+            { B + parts[7].off }, { B + parts[8].off }, { B + parts[9].off }, { B + parts[10].off }, { B + parts[11].off } };
+        d.scene.table = dd.table.p(); d.scene.small = dd.small.p(); d.scene.small_idx = dd.small_idx.p(); d.scene.np = np; d.scene.n_rec = (ns + 3) / 4;
         d.scene.filter_R2 = R2f; d.scene.filter_sigma = (float)(16.0 * 5.9604644775390625e-08 * std::max(rmax, 1e-3));
-        d.scene.big = d.big.p; d.scene.big_idx = d.big_idx.p; d.scene.nb = nb;
-        d.scene.sph = d.sph.p; d.scene.sphd = d.sphd.p; d.scene.mat = d.mat.p; d.scene.matd = d.matd.p; d.scene.kind = d.kind.p; d.scene.n = n;
-        d.scene.u_bimg = d.ubimg.p; d.scene.u_npad = u_npad; d.scene.u_sc = u_sc; d.scene.bigf = bigf_ok ? d.bigf.p : nullptr;
+        d.scene.big = dd.big.p(); d.scene.big_idx = dd.big_idx.p(); d.scene.nb = nb;
+        d.scene.sph = dd.sph.p(); d.scene.sphd = dd.sphd.p(); d.scene.mat = dd.mat.p(); d.scene.matd = dd.matd.p(); d.scene.kind = dd.kind.p(); d.scene.n = n;
+        d.scene.u_bimg = dd.ubimg.p(); d.scene.u_npad = u_npad; d.scene.u_sc = u_sc; d.scene.bigf = bigf_ok ? dd.bigf.p() : nullptr;
         d.has_scene = true;
         c->scene_bytes = bytes;
     }
@@ -812,7 +838,8 @@ static int render_frame(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_param
     DeviceState& d0 = c->dev[0];
     uint32_t launches = 0;
     CU(cudaSetDevice(d0.device));
-    if (d0.pinned_bytes < frame_bytes) {
+    const bool direct = host_is_pinned(out_rgba);           // a page-locked caller buffer takes the DMA directly (no staging copy)
+    if (!direct && d0.pinned_bytes < frame_bytes) {
         if (d0.pinned) cudaFreeHost(d0.pinned);
         d0.pinned = nullptr; d0.pinned_bytes = 0;
         CU(cudaMallocHost(&d0.pinned, frame_bytes)); d0.pinned_bytes = frame_bytes;
@@ -883,10 +910,10 @@ static int render_frame(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_param
         c->gather_note = note;
         d_final = d0.frame.p;
     }
-    CU(cudaMemcpyAsync(d0.pinned, d_final, frame_bytes, cudaMemcpyDeviceToHost, d0.stream));
+    CU(cudaMemcpyAsync(direct ? out_rgba : d0.pinned, d_final, frame_bytes, cudaMemcpyDeviceToHost, d0.stream));
     CU(cudaMemcpyAsync(d0.pinned_cnt, d0.counters.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d0.stream));
     CU(cudaStreamSynchronize(d0.stream));
-    memcpy(out_rgba, d0.pinned, frame_bytes);
+    if (!direct) memcpy(out_rgba, d0.pinned, frame_bytes);
     if (stats) {
         memset(stats, 0, sizeof *stats);
         float ms = 0; CU(cudaEventElapsedTime(&ms, d0.ev0, d0.ev1));
@@ -1116,13 +1143,17 @@ static int render_rank_impl(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_p
         }
         c->gather_note = note;
     }
+    // a caller's frame buffer that is page-locked itself (cudaHostAlloc / cudaHostRegister, torch pin_memory) takes the DMA directly;
+    // pageable memory goes through the ctx's pinned staging buffer and one host memcpy (0.3 ms for the 3.2 MB headline frame)
+    bool direct = false;
     if (out_rgba && frame_here) {
-        if (d.pinned_bytes < frame_bytes) {
+        direct = host_is_pinned(out_rgba);
+        if (!direct && d.pinned_bytes < frame_bytes) {
             if (d.pinned) cudaFreeHost(d.pinned);
             d.pinned = nullptr; d.pinned_bytes = 0;
             CU(cudaMallocHost(&d.pinned, frame_bytes)); d.pinned_bytes = frame_bytes;
         }
-        CU(cudaMemcpyAsync(d.pinned, d_final, frame_bytes, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(direct ? out_rgba : d.pinned, d_final, frame_bytes, cudaMemcpyDeviceToHost, st));
     }
     CU(cudaMemcpyAsync(d.pinned_cnt, d.counters.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     if (enqueue_only) {                                     // no host synchronisation: rtiow_ctx_synchronize collects the stats
@@ -1133,7 +1164,7 @@ static int render_rank_impl(rtiow_ctx* c, const rtiow_camera* cam, const rtiow_p
         return RTIOW_OK;
     }
     CU(cudaStreamSynchronize(st));
-    if (out_rgba && frame_here) memcpy(out_rgba, d.pinned, frame_bytes);
+    if (out_rgba && frame_here && !direct) memcpy(out_rgba, d.pinned, frame_bytes);
     if (d_frame_out) *d_frame_out = frame_here ? d_final : nullptr;
     if (stats) {
         memset(stats, 0, sizeof *stats);

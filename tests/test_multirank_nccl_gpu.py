@@ -86,3 +86,22 @@ def test_enqueued_frames_equal_the_synchronous_call(capi, final_scene):
         assert rc.synchronize()["kernel_launches"] == 0                      # nothing enqueued since
         again, _ = rc.render_rank(cam, prms[0])
         assert np.array_equal(again, refs[0])
+
+
+def test_page_locked_caller_buffer_takes_the_frame_directly(capi, final_scene):
+    """a pinned out_rgba (cudaHostAlloc / torch pin_memory) receives the D2H copy without the staging memcpy: same bytes, both entry points"""
+    _need(capi, 1)
+    torch = pytest.importorskip("torch")
+    W, H = 200, 113
+    cam = final_camera(capi, W / H)
+    prm = capi.default_params(width=W, height=H, spp=3, seed=9)
+    pinned = torch.zeros((H, W, 4), dtype=torch.uint8, pin_memory=True).numpy()
+    with capi.Context(device=0, rank=0, world=1) as rc, capi.Context(1) as one:
+        rc.upload_scene(**final_scene[0]); one.upload_scene(**final_scene[0])
+        ref, _ = one.render(cam, prm)
+        a, _ = rc.render_rank(cam, prm, out=pinned)
+        assert a is pinned and np.array_equal(pinned, ref)
+        pinned[:] = 0
+        b, _ = one.render(cam, prm, out=pinned)
+        assert np.array_equal(b, ref)
+
