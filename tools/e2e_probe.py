@@ -1,5 +1,8 @@
+"""Where the end-to-end call spends its time beyond the kernel: rtiow_scene_upload, rtiow_render_rank into a page-locked and into a
+pageable frame buffer, rtiow_render_rank_device (GPU box).    python tools/e2e_probe.py"""
 import sys, time
-sys.path.insert(0, '/root/repo')
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import numpy as np, torch
 from rtiow_b200 import capi
 scene = capi.random_scene(1)
