@@ -4,6 +4,14 @@ from pathlib import Path
 import numpy as np
 import pytest
 
+# torch first, when it is there: it maps its own bundled libnccl.so.2, which librtiow_cuda.so then shares (as under bench.py).  The
+# other order breaks `import torch` later in the same process: on a multi-GPU box the library's gathers dlopen the SYSTEM
+# libnccl.so.2 (an older build), and the loader hands that one to libtorch_cuda.so, which needs symbols it does not have.
+try:
+    import torch  # noqa: F401
+except Exception:  # the CPU-only suite and the library do not need it
+    torch = None
+
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
